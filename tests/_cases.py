@@ -1,0 +1,54 @@
+"""Shared description of the golden cases written by tools/make_golden.py
+(inputs are re-derived from seeds; outputs come from the reference)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import nerf_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name + ".npz")).items()}
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _pc():
+    return O.make_params(0, use_viewdirs=True, output_ch=5)
+
+
+def _pf():
+    return O.make_params(1, use_viewdirs=True, output_ch=5)
+
+
+# tag -> (coarse params, fine params, kwargs of the render)
+RENDER_CASES = {
+    "render_c0": dict(pc=lambda: O.make_params(100, use_viewdirs=False, input_ch_views=0, output_ch=4), pf=None,
+                      use_viewdirs=False, N_samples=64, N_importance=0, white_bkgd=False, ndc=False, lindisp=False),
+    "render_c1": dict(pc=_pc, pf=_pf, use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=True,
+                      ndc=False, lindisp=False),
+    "render_c1_sharp": dict(pc=lambda: O.sharpen_density(_pc()), pf=lambda: O.sharpen_density(_pf()),
+                            use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=True, ndc=False,
+                            lindisp=False),
+    "render_lindisp": dict(pc=lambda: O.sharpen_density(_pc()), pf=lambda: O.sharpen_density(_pf()),
+                           use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=False, ndc=False,
+                           lindisp=True),
+    "render_llff": dict(pc=lambda: O.sharpen_density(_pc()), pf=lambda: O.sharpen_density(_pf()),
+                        use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=False, ndc=True,
+                        lindisp=False),
+    "render_nov_40_24": dict(
+        pc=lambda: O.sharpen_density(O.make_params(7, use_viewdirs=False, input_ch_views=0, output_ch=5)),
+        pf="same", use_viewdirs=False, N_samples=40, N_importance=24, white_bkgd=True, ndc=False, lindisp=False),
+}
+
+
+def case_params(tag):
+    c = RENDER_CASES[tag]
+    pc = c["pc"]()
+    pf = pc if c["pf"] == "same" else (c["pf"]() if c["pf"] is not None else None)
+    return pc, pf

@@ -1,0 +1,117 @@
+"""Pins the CPU oracle (oracle/) to outputs of the unmodified reference
+(tests/golden/*.npz, written by tools/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from oracle import sample_pdf_np as SP
+from _cases import RENDER_CASES, T, case_params, gold
+
+torch.set_num_threads(8)
+
+
+def close(a, b, tol):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=0, atol=tol)
+
+
+def test_get_rays_and_ndc_bit_exact():
+    g = gold("rays")
+    ro, rd = O.get_rays(20, 24, g["Kb"], T(g["c2wb"]))
+    assert np.array_equal(ro.numpy(), g["rays_o_b"]) and np.array_equal(rd.numpy(), g["rays_d_b"])
+    ro, rd = O.get_rays(18, 24, g["Kl"], T(g["c2wl"]))
+    assert np.array_equal(rd.numpy(), g["rays_d_l"])
+    no, nd = O.ndc_rays(18, 24, g["Kl"][0][0], 1.0, ro, rd)
+    assert np.array_equal(no.numpy(), g["ndc_o"]) and np.array_equal(nd.numpy(), g["ndc_d"])
+
+
+def test_embed_bit_exact():
+    g = gold("embed")
+    assert int(g["d10"]) == 63 and int(g["d4"]) == 27
+    assert np.array_equal(O.embed(T(g["x"]), 10).numpy(), g["e10"])
+    assert np.array_equal(O.embed(T(g["x"]), 4).numpy(), g["e4"])
+
+
+def test_mlp_forward():
+    g = gold("mlp")
+    pv = O.to_torch(O.make_params(int(g["seed_v"]), use_viewdirs=True))
+    pn = O.to_torch(O.make_params(int(g["seed_n"]), use_viewdirs=False, input_ch_views=0, output_ch=5))
+    x = T(g["x"])
+    close(O.mlp_forward(pv, x), g["out_v"], 1e-6)
+    close(O.mlp_forward(pn, x[:, :63], input_ch_views=0, use_viewdirs=False), g["out_n"], 1e-6)
+
+
+@pytest.mark.parametrize("wb", [0, 1])
+def test_raw2outputs_bit_exact(wb):
+    g = gold("raw2outputs")
+    out = O.raw2outputs(T(g["raw"]), T(g["z"]), T(g["rays_d"]), 0, bool(wb))
+    for name, v in zip(("rgb", "disp", "acc", "weights", "depth"), out):
+        assert np.array_equal(v.numpy(), g[f"{name}_wb{wb}"]), name
+
+
+def test_sample_pdf_torch_restatement_bit_exact():
+    g = gold("sample_pdf")
+    s, i = O.sample_pdf(T(g["bins"]), T(g["weights"]), 128, det=True, return_inds=True)
+    assert np.array_equal(i.numpy(), g["i128"].astype(np.int64))
+    assert np.array_equal(s.numpy(), g["s128"])
+    s, i = O.sample_pdf(T(g["bins"]), T(g["weights"]), 64, det=True, return_inds=True)
+    assert np.array_equal(i.numpy(), g["i64"].astype(np.int64)) and np.array_equal(s.numpy(), g["s64"])
+    s, i = O.sample_pdf(T(g["bins"]), T(g["weights"]), 128, det=False, u=T(g["urand"]), return_inds=True)
+    assert np.array_equal(i.numpy(), g["irand"].astype(np.int64)) and np.array_equal(s.numpy(), g["srand"])
+
+
+def test_sample_pdf_numpy_bit_level_restatement():
+    """The arithmetic contract the CUDA kernel follows (sum order, fp64 scan,
+    linspace fma, un-fused lerp) reproduces the reference bit for bit."""
+    g = gold("sample_pdf")
+    s, i, cdf = SP.sample_pdf_np(g["bins"], g["weights"], 128)
+    assert np.array_equal(cdf, g["cdf"])
+    assert np.array_equal(i, g["i128"].astype(np.int64))
+    assert np.array_equal(s, g["s128"])
+    s, i, _ = SP.sample_pdf_np(g["bins"], g["weights"], 64)
+    assert np.array_equal(i, g["i64"].astype(np.int64)) and np.array_equal(s, g["s64"])
+    s, i, _ = SP.sample_pdf_np(g["bins"], g["weights"], 128, u=g["urand"])
+    assert np.array_equal(i, g["irand"].astype(np.int64)) and np.array_equal(s, g["srand"])
+    assert np.array_equal(SP.torch_linspace01_f32(64), torch.linspace(0., 1., 64).numpy())
+    assert np.array_equal(SP.torch_linspace01_f32(40), torch.linspace(0., 1., 40).numpy())
+
+
+@pytest.mark.parametrize("tag", sorted(RENDER_CASES))
+def test_render_matches_reference(tag):
+    g = gold(tag)
+    c = RENDER_CASES[tag]
+    pc, pf = case_params(tag)
+    out = O.render(int(g["H"]), int(g["W"]), g["K"], O.to_torch(pc), O.to_torch(pf) if pf is not None else None,
+                   rays=(T(g["rays_o"]), T(g["rays_d"])), ndc=c["ndc"], near=float(g["near"]), far=float(g["far"]),
+                   use_viewdirs=c["use_viewdirs"], N_samples=c["N_samples"], N_importance=c["N_importance"],
+                   lindisp=c["lindisp"], white_bkgd=c["white_bkgd"], retraw=True)
+    tol = 2e-6
+    close(out["raw"], g["raw"], 2e-5)
+    for k in ("rgb_map", "acc_map"):
+        close(out[k], g[k], tol)
+    np.testing.assert_allclose(out["disp_map"].numpy(), g["disp_map"], rtol=1e-5, atol=1e-6)
+    if c["N_importance"] > 0:
+        assert np.array_equal(out["inds"].numpy(), g["inds"].astype(np.int64))
+        for k in ("rgb0", "acc0", "z_std"):
+            close(out[k], g[k], tol)
+
+
+def test_train_grads_match_reference():
+    g = gold("train_grads")
+    pc, pf = case_params("render_c1_sharp")
+    K1, _ = O.blender_camera(800, 800, 30.0)
+    rays, _ = O.pack_rays(T(g["rays_o"]), T(g["rays_d"]), 2.0, 6.0, use_viewdirs=True)
+    loss, gc, gf, _ = O.train_loss_and_grads(rays, T(g["target"]), O.to_torch(pc), O.to_torch(pf),
+                                             N_samples=64, N_importance=128, white_bkgd=True)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    for tag, grads in (("c", gc), ("f", gf)):
+        for name, gr in grads.items():
+            key = f"{tag}.{name}"
+            n = float(g[key + ".norm"])
+            assert abs(float(gr.double().norm()) - n) <= 1e-4 * max(n, 1e-6), key
+            if key + ".full" in g:
+                np.testing.assert_allclose(gr.numpy(), g[key + ".full"], rtol=1e-3, atol=1e-7 + 1e-4 * n)
+            else:
+                np.testing.assert_allclose(gr.reshape(-1).numpy()[g[key + ".idx"]], g[key + ".val"],
+                                           rtol=1e-3, atol=1e-7 + 1e-4 * n)
