@@ -1,0 +1,195 @@
+/*
+ * nerf_b200.h -- C ABI of libnerf_b200.so: the B200 (sm_100a) implementation
+ * of the original-NeRF render/train hot path of isaacchunn/nerf-projects.
+ *
+ * The reference has no FFI of its own for this path (it is eager PyTorch called
+ * from notebook cells), so this ABI is the inner boundary that the Python
+ * drop-in (`nerf_projects_b200`, same names/signatures as the notebook
+ * functions) binds with ctypes.  Each entry point names the reference code it
+ * replaces; "ipynb:N" is the raw JSON line number of
+ * /root/reference/nerf/nerf.ipynb, other paths are relative to
+ * /root/reference/nerf/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (caller-allocated, e.g. torch tensor
+ *     storage) unless the parameter name starts with `h_`;
+ *   - tensors are dense row-major fp32 unless a leading dimension `ld*`
+ *     (in elements) is given;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     no call synchronises the device;
+ *   - return value: 0 on success, negative on error; the message of the last
+ *     error on the calling thread is returned by nerfb_last_error();
+ *   - no C++ exceptions cross this boundary, no torch types appear in it.
+ */
+#ifndef NERF_B200_H_
+#define NERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFB_ABI_VERSION 1
+
+enum {
+  NERFB_OK = 0,
+  NERFB_ERR_ARG = -1,     /* invalid argument / unsupported shape */
+  NERFB_ERR_CUDA = -2,    /* CUDA runtime error (launch, attribute, ...) */
+  NERFB_ERR_ARCH = -3     /* device is not sm_100 */
+};
+
+int nerfb_abi_version(void);
+const char* nerfb_last_error(void);
+/* sm count / compute capability of the current device */
+int nerfb_device_info(int* h_sm_count, int* h_cc_major, int* h_cc_minor);
+
+/* ------------------------------------------------------------------ rays */
+
+/* get_rays (nerf_helpers.py:222-296): one pinhole ray per pixel, integer pixel
+ * coordinates, dirs=((i-cx)/fx, -(j-cy)/fy, -1) rotated by c2w[:3,:3].
+ * c2w: [3,4] row-major.  rays_o, rays_d: [H*W,3]. */
+int nerfb_get_rays(int H, int W, float fx, float fy, float cx, float cy,
+                   const float* c2w, float* rays_o, float* rays_d, void* stream);
+
+/* ndc_rays (nerf_helpers.py:311-369), n rays, in place allowed. */
+int nerfb_ndc_rays(int n, int H, int W, double focal, double near_plane,
+                   const float* rays_o, const float* rays_d,
+                   float* out_o, float* out_d, void* stream);
+
+/* Ray packing of render() (ipynb:598-629): viewdirs = d/|d| taken from
+ * `view_d` (the pre-NDC directions; may equal rays_d), optional NDC warp with
+ * near=1 and focal, then rows [o(3) d(3) near far (viewdir(3))].
+ * out: [n, 8] or [n, 11] when use_viewdirs. */
+int nerfb_pack_rays(int n, const float* rays_o, const float* rays_d, const float* view_d,
+                    int use_viewdirs, int ndc, int H, int W, double focal,
+                    float near_v, float far_v, float* out, void* stream);
+
+/* Coarse depths of render_rays (ipynb:418-444): t=linspace(0,1,S);
+ * z = near(1-t)+far t, or 1/(1/near(1-t)+1/far t) when lindisp; when t_rand
+ * ([R,S], uniform [0,1)) is not NULL the stratified jitter is applied.
+ * rays: packed rows of width ray_width (near/far at columns 6,7). z: [R,S]. */
+int nerfb_coarse_z(int R, int S, const float* rays, int ray_width, int lindisp,
+                   const float* t_rand, float* z, void* stream);
+
+/* ------------------------------------------------- positional encoding */
+
+/* Embedder.embed (embedder.py:36-80): out[i, col0 : col0+3+6L] =
+ * [x, sin(2^0 x), cos(2^0 x), ..., cos(2^(L-1) x)]; L < 0 -> identity (3). */
+int nerfb_embed(int n, const float* x, int ldx, int L, float* out, int ld_out, int col0,
+                void* stream);
+
+/* run_network's input stage (ipynb:824-843) fused with pts = o + d z
+ * (ipynb:447): writes gamma(pts) for all R*S samples into
+ * enc[:, col_pts : col_pts+3+6L] and, when Lv != NERFB_NO_VIEWS, gamma(viewdir)
+ * broadcast to every sample of the ray into enc_dir[:, col_dir : ...].
+ * If `pts` is not NULL it is used instead of o + d z ([R*S,3]); `viewdirs`
+ * ([R,3]) overrides columns 8..10 of `rays` when not NULL. */
+#define NERFB_NO_VIEWS (-1000)
+int nerfb_embed_samples(int R, int S, const float* rays, int ray_width, const float* z,
+                        const float* pts, const float* viewdirs, int L, int Lv,
+                        float* enc, int ld_enc, int col_pts,
+                        float* enc_dir, int ld_dir, int col_dir, void* stream);
+
+/* ------------------------------------------- fp32 validation-mode layers */
+
+/* nn.Linear (+ReLU) forward, nerf.py:70-109: Y[M,N] = act(X[M,K] W[N,K]^T + b). */
+int nerfb_linear_fwd(int M, int N, int K, const float* X, int ldx, const float* W, int ldw,
+                     const float* b, float* Y, int ldy, int relu, void* stream);
+/* dX[M,K] (= or +=) dY[M,N] W[N,K]; then, if relu_src != NULL, dX *= (relu_src > 0)
+ * (relu_src is the post-ReLU activation that fed this layer). */
+int nerfb_linear_bwd_data(int M, int N, int K, const float* dY, int lddy, const float* W, int ldw,
+                          float* dX, int lddx, const float* relu_src, int ld_relu,
+                          int accumulate, void* stream);
+/* dW[N,K] += dY[M,N]^T X[M,K];  db[N] += column sums of dY (db may be NULL). */
+int nerfb_linear_bwd_weight(int M, int N, int K, const float* dY, int lddy, const float* X, int ldx,
+                            float* dW, int lddw, float* db, void* stream);
+
+/* ------------------------------------------------------------ compositing */
+
+/* raw2outputs forward (ipynb:254-349).  raw: [R,S,raw_ch] (raw_ch >= 4, channels
+ * 0..2 rgb logits, 3 sigma); z: [R,S]; rays_d: rows of stride ld_d (|d| scales
+ * the intervals; last interval 1e10); noise: NULL or [R,S] added to sigma.
+ * Outputs (any may be NULL except rgb): rgb[R,3] disp[R] acc[R] weights[R,S] depth[R]. */
+int nerfb_raw2outputs_fwd(int R, int S, const float* raw, int raw_ch, const float* z,
+                          const float* rays_d, int ld_d, const float* noise, int white_bkgd,
+                          float* rgb, float* disp, float* acc, float* weights, float* depth,
+                          void* stream);
+/* Backward of the above w.r.t. raw.  Upstream grads may be NULL (treated as 0).
+ * d_raw: [R,S,raw_ch] (channels >= 4 are written as 0). */
+int nerfb_raw2outputs_bwd(int R, int S, const float* raw, int raw_ch, const float* z,
+                          const float* rays_d, int ld_d, const float* noise, int white_bkgd,
+                          const float* d_rgb, const float* d_disp, const float* d_acc,
+                          const float* d_weights, const float* d_depth,
+                          float* d_raw, void* stream);
+
+/* --------------------------------------------------- hierarchical sampling */
+
+/* sample_pdf (nerf_helpers.py:372-439), one warp per ray, reproducing the
+ * reference's CPU fp32 arithmetic bit for bit (see oracle/sample_pdf_np.py):
+ * bins[R,M] (stride ld_bins), weights[R,M-1] (stride ld_w).  det!=0 ->
+ * u=linspace(0,1,N); else u must be given ([R,N]).  samples[R,N];
+ * inds (int64 [R,N]) may be NULL. */
+int nerfb_sample_pdf(int R, int M, int N, const float* bins, int ld_bins,
+                     const float* weights, int ld_w, int det, const float* u,
+                     float* samples, long long* inds, void* stream);
+
+/* The hierarchical step of render_rays (ipynb:459-467, 486) in one kernel:
+ * z_mid = .5(z[1:]+z[:-1]); z_samples = sample_pdf(z_mid, weights[1:-1], N);
+ * z_out = sort(cat(z, z_samples)); z_std = std(z_samples, unbiased=False).
+ * z, weights: [R,S]; z_out: [R,S+N]; z_samples/inds/z_std may be NULL. */
+int nerfb_hierarchical_z(int R, int S, int N, const float* z, const float* weights,
+                         int det, const float* u, float* z_out, float* z_samples,
+                         long long* inds, float* z_std, void* stream);
+
+/* ------------------------------------------- fused tensor-core MLP (bf16) */
+
+/* Canonical NeRF MLP only: D=8, W=256, skips=[4], multires 10 (63 ch),
+ * multires_views 4 (27 ch) or no view directions. */
+size_t nerfb_packed_weights_bytes(int use_viewdirs);
+/* Packs one network's fp32 parameters (nerf.py:32-55 state_dict order, see
+ * NERFB_PARAM_* below) into the bf16 UMMA shared-memory images the fused
+ * kernel streams with bulk async copies.  h_params: host array of device
+ * pointers, NERFB_NUM_PARAMS entries; entries not used by the architecture
+ * may be NULL.  out_ch = rows of output_linear (4 or 5) when !use_viewdirs. */
+enum {
+  NERFB_P_PTS0_W = 0, NERFB_P_PTS0_B, /* ... pts_linears.i at 2i, 2i+1 for i<8 */
+  NERFB_P_VIEWS_W = 16, NERFB_P_VIEWS_B,
+  NERFB_P_FEATURE_W, NERFB_P_FEATURE_B,
+  NERFB_P_ALPHA_W, NERFB_P_ALPHA_B,
+  NERFB_P_RGB_W, NERFB_P_RGB_B,
+  NERFB_P_OUTPUT_W, NERFB_P_OUTPUT_B,
+  NERFB_NUM_PARAMS
+};
+int nerfb_pack_weights(const float* const* h_params, int use_viewdirs, int out_ch,
+                       void* packed, void* stream);
+/* run_network + NeRF.forward (ipynb:790-855, nerf.py:57-111) for all R*S
+ * samples: encoding in registers, 8x256 MLP + heads on tcgen05 tensor cores
+ * (bf16 operands, fp32 TMEM accumulators, fp32 density head), activations
+ * never leave the SM.  Sample positions are o + d z from `rays`/`z`, or the
+ * explicit `pts` ([R*S,3]) when not NULL; `viewdirs` as in nerfb_embed_samples.
+ * raw: [R*S, 4] = [rgb logits, sigma]. */
+int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const float* z,
+                       const float* pts, const float* viewdirs, int use_viewdirs,
+                       const void* packed, float* raw, void* stream);
+/* Self-test of the tcgen05 building blocks (descriptor/swizzle/TMEM layout):
+ * C[128,N] = A[128,K] B[N,K]^T with bf16-rounded inputs, K multiple of 64,
+ * N multiple of 16 <= 256.  Used by tests only. */
+int nerfb_umma_selftest(int N, int K, const float* A, const float* B, float* C, void* stream);
+
+/* ------------------------------------------------------------- optimiser */
+
+/* torch.optim.Adam step (ipynb:905, 1275) for up to NERFB_ADAM_MAX tensors in
+ * one launch: p -= lr * mhat / (sqrt(vhat) + eps), with g scaled by grad_scale
+ * first.  h_* are host arrays of device pointers / sizes. */
+#define NERFB_ADAM_MAX 64
+int nerfb_adam_step(int n_tensors, float* const* h_p, const float* const* h_g,
+                    float* const* h_m, float* const* h_v, const long long* h_numel,
+                    float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libnerf_b200.so (C ABI declared in include/nerf_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails the
+product raises -- it never routes through PyTorch eager ops or the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
+
+NERFB_NO_VIEWS = -1000
+NERFB_NUM_PARAMS = 26
+NERFB_ADAM_MAX = 64
+
+_vp, _i, _f, _d, _ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
+
+_SIGS = {
+    "nerfb_abi_version": ([], _i),
+    "nerfb_last_error": ([], C.c_char_p),
+    "nerfb_device_info": ([C.POINTER(_i)] * 3, _i),
+    "nerfb_get_rays": ([_i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
+    "nerfb_ndc_rays": ([_i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_pack_rays": ([_i, _vp, _vp, _vp, _i, _i, _i, _i, _d, _f, _f, _vp, _vp], _i),
+    "nerfb_coarse_z": ([_i, _i, _vp, _i, _i, _vp, _vp, _vp], _i),
+    "nerfb_embed": ([_i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
+    "nerfb_embed_samples": ([_i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
+    "nerfb_linear_fwd": ([_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp], _i),
+    "nerfb_linear_bwd_data": ([_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp], _i),
+    "nerfb_linear_bwd_weight": ([_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp], _i),
+    "nerfb_raw2outputs_fwd": ([_i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_raw2outputs_bwd": ([_i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_sample_pdf": ([_i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_hierarchical_z": ([_i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_packed_weights_bytes": ([_i], C.c_size_t),
+    "nerfb_pack_weights": ([C.POINTER(_vp), _i, _i, _vp, _vp], _i),
+    "nerfb_mlp_fwd_bf16": ([_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "nerfb_umma_selftest": ([_i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_adam_step": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll),
+                         _f, _f, _f, _f, _i, _f, _vp], _i),
+}
+
+_lib = None
+
+
+class NerfB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NerfB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m nerf_projects_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (args, res) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.argtypes = args
+        fn.restype = res
+    if lib.nerfb_abi_version() != 1:
+        raise NerfB200Error("libnerf_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().nerfb_last_error().decode(errors="replace")
+        raise NerfB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NerfB200Error("nerf_projects_b200 kernels need CUDA tensors; got a tensor on %s "
+                                "(there is no CPU path)" % t.device)
+
+
+def f32c(t):
+    """contiguous fp32 view/copy"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()

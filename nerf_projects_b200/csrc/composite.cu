@@ -1,0 +1,210 @@
+// Alpha compositing: raw2outputs (ipynb:254-349) forward and its backward
+// w.r.t. raw.  One warp per ray; the exclusive transmittance product is a warp
+// scan in fp64 rounded to fp32 per sample, which is what torch.cumprod does on
+// CPU (double running product).
+#include "common.cuh"
+
+namespace nerfb {
+
+constexpr int CW = 4;  // warps per block
+
+__device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
+  const float x = __ldg(d), y = __ldg(d + 1), z = __ldg(d + 2);
+  return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Computes alpha_i, x_i = 1-alpha_i+1e-10 and the exclusive product T_i for one
+// ray; results for sample i are handed to `emit(i, alpha, x, T)` in order of
+// 32-sample chunks.
+template <typename Emit>
+__device__ __forceinline__ void scan_ray(int S, const float* __restrict__ raw, int ch,
+                                         const float* __restrict__ z, float nrm,
+                                         const float* __restrict__ noise, int lane, Emit emit) {
+  double carry = 1.0;
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    float alpha = 0.f, x = 1.f;
+    if (i < S) {
+      float dist = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+      dist = __fmul_rn(dist, nrm);
+      float s = raw[(size_t)i * ch + 3];
+      if (noise) s = __fadd_rn(s, noise[i]);
+      const float act = fmaxf(s, 0.f);
+      alpha = __fsub_rn(1.0f, expf(__fmul_rn(-act, dist)));
+      x = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    }
+    // inclusive product scan over the chunk (fp64)
+    double p = (double)x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double q = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) p *= q;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.0;
+    // torch.cumprod keeps a double running product and rounds each output
+    const float T = (float)(carry * excl);
+    if (i < S) emit(i, alpha, x, T);
+    carry *= __shfl_sync(0xffffffffu, p, 31);
+  }
+}
+
+__global__ void __launch_bounds__(32 * CW)
+raw2outputs_fwd_kernel(int R, int S, const float* __restrict__ raw, int ch, const float* __restrict__ z,
+                       const float* __restrict__ rays_d, int ld_d, const float* __restrict__ noise,
+                       int white, float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
+                       float* __restrict__ weights, float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * CW + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* rr = raw + (size_t)r * S * ch;
+  const float* zr = z + (size_t)r * S;
+  const float* nr = noise ? noise + (size_t)r * S : nullptr;
+  const float nrm = ray_norm(rays_d + (size_t)r * ld_d);
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, dsum = 0.f, asum = 0.f;
+  float* wr = weights ? weights + (size_t)r * S : nullptr;
+  scan_ray(S, rr, ch, zr, nrm, nr, lane, [&](int i, float alpha, float x, float T) {
+    const float w = __fmul_rn(alpha, T);
+    if (wr) wr[i] = w;
+    c0 += w * sigmoidf_(rr[(size_t)i * ch + 0]);
+    c1 += w * sigmoidf_(rr[(size_t)i * ch + 1]);
+    c2 += w * sigmoidf_(rr[(size_t)i * ch + 2]);
+    dsum += w * zr[i];
+    asum += w;
+  });
+  c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dsum = warp_sum(dsum); asum = warp_sum(asum);
+  if (lane == 0) {
+    if (white) {
+      const float bg = __fsub_rn(1.0f, asum);
+      c0 += bg; c1 += bg; c2 += bg;
+    }
+    rgb[3 * r + 0] = c0; rgb[3 * r + 1] = c1; rgb[3 * r + 2] = c2;
+    if (depth) depth[r] = dsum;
+    if (acc) acc[r] = asum;
+    if (disp) disp[r] = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(dsum, fmaxf(1e-10f, asum)), 1e-10f));
+  }
+}
+
+__global__ void __launch_bounds__(32 * CW)
+raw2outputs_bwd_kernel(int R, int S, const float* __restrict__ raw, int ch, const float* __restrict__ z,
+                       const float* __restrict__ rays_d, int ld_d, const float* __restrict__ noise,
+                       int white, const float* __restrict__ d_rgb, const float* __restrict__ d_disp,
+                       const float* __restrict__ d_acc, const float* __restrict__ d_weights,
+                       const float* __restrict__ d_depth, float* __restrict__ d_raw) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * CW + wib;
+  if (r >= R) return;
+  float* s_alpha = smem + (size_t)wib * 3 * S;
+  float* s_x = s_alpha + S;
+  float* s_T = s_x + S;
+  const float* rr = raw + (size_t)r * S * ch;
+  const float* zr = z + (size_t)r * S;
+  const float* nr = noise ? noise + (size_t)r * S : nullptr;
+  const float nrm = ray_norm(rays_d + (size_t)r * ld_d);
+
+  float dsum = 0.f, asum = 0.f;
+  scan_ray(S, rr, ch, zr, nrm, nr, lane, [&](int i, float alpha, float x, float T) {
+    s_alpha[i] = alpha; s_x[i] = x; s_T[i] = T;
+    const float w = __fmul_rn(alpha, T);
+    dsum += w * zr[i];
+    asum += w;
+  });
+  dsum = warp_sum(dsum); asum = warp_sum(asum);
+  __syncwarp();
+
+  const float g0 = d_rgb ? d_rgb[3 * r + 0] : 0.f, g1 = d_rgb ? d_rgb[3 * r + 1] : 0.f,
+              g2 = d_rgb ? d_rgb[3 * r + 2] : 0.f;
+  float g_depth = d_depth ? d_depth[r] : 0.f;
+  float g_acc = d_acc ? d_acc[r] : 0.f;
+  if (white) g_acc -= (g0 + g1 + g2);
+  if (d_disp) {
+    const float denom = fmaxf(1e-10f, asum);
+    const float q = dsum / denom;
+    if (q > 1e-10f) {
+      const float gq = -d_disp[r] / (q * q);
+      g_depth += gq / denom;
+      if (asum > 1e-10f) g_acc += -gq * dsum / (denom * denom);
+    }
+  }
+  const float* gwr = d_weights ? d_weights + (size_t)r * S : nullptr;
+  float* out = d_raw + (size_t)r * S * ch;
+
+  // reverse pass: suffix[i] = sum_{k>i} gw_k * w_k
+  float carry = 0.f;
+  const int nchunk = (S + 31) / 32;
+  for (int cidx = nchunk - 1; cidx >= 0; --cidx) {
+    const int i = cidx * 32 + lane;
+    float gw = 0.f, w = 0.f, alpha = 0.f, x = 1.f, T = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (i < S) {
+      alpha = s_alpha[i]; x = s_x[i]; T = s_T[i];
+      w = alpha * T;
+      s0 = sigmoidf_(rr[(size_t)i * ch + 0]);
+      s1 = sigmoidf_(rr[(size_t)i * ch + 1]);
+      s2 = sigmoidf_(rr[(size_t)i * ch + 2]);
+      gw = g0 * s0 + g1 * s1 + g2 * s2 + g_depth * zr[i] + g_acc + (gwr ? gwr[i] : 0.f);
+    }
+    const float v = gw * w;
+    // inclusive suffix scan within the chunk
+    float sfx = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float q = __shfl_down_sync(0xffffffffu, sfx, o);
+      if (lane + o < 32) sfx += q;
+    }
+    const float after = sfx - v + carry;  // strictly after i
+    if (i < S) {
+      const float g_alpha = gw * T - after / x;
+      float dist = (i + 1 < S) ? __fsub_rn(zr[i + 1], zr[i]) : 1e10f;
+      dist = __fmul_rn(dist, nrm);
+      float s = rr[(size_t)i * ch + 3];
+      if (nr) s = __fadd_rn(s, nr[i]);
+      float g_sigma = 0.f;
+      if (s > 0.f) g_sigma = g_alpha * (1.0f - alpha) * dist;  // exp(-s*dist) = 1-alpha
+      out[(size_t)i * ch + 0] = g0 * w * s0 * (1.f - s0);
+      out[(size_t)i * ch + 1] = g1 * w * s1 * (1.f - s1);
+      out[(size_t)i * ch + 2] = g2 * w * s2 * (1.f - s2);
+      out[(size_t)i * ch + 3] = g_sigma;
+      for (int c = 4; c < ch; ++c) out[(size_t)i * ch + c] = 0.f;
+    }
+    carry += __shfl_sync(0xffffffffu, sfx, 0);
+  }
+}
+
+}  // namespace nerfb
+
+using namespace nerfb;
+
+extern "C" int nerfb_raw2outputs_fwd(int R, int S, const float* raw, int raw_ch, const float* z,
+                                     const float* rays_d, int ld_d, const float* noise, int white_bkgd,
+                                     float* rgb, float* disp, float* acc, float* weights, float* depth,
+                                     void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && raw && z && rays_d && rgb && raw_ch >= 4 && ld_d >= 3,
+                "nerfb_raw2outputs_fwd: bad arguments");
+  if (R == 0) return NERFB_OK;
+  raw2outputs_fwd_kernel<<<cdiv(R, CW), 32 * CW, 0, as_stream(stream)>>>(R, S, raw, raw_ch, z, rays_d, ld_d, noise,
+                                                                        white_bkgd, rgb, disp, acc, weights, depth);
+  return check_launch("raw2outputs_fwd_kernel");
+}
+
+extern "C" int nerfb_raw2outputs_bwd(int R, int S, const float* raw, int raw_ch, const float* z,
+                                     const float* rays_d, int ld_d, const float* noise, int white_bkgd,
+                                     const float* d_rgb, const float* d_disp, const float* d_acc,
+                                     const float* d_weights, const float* d_depth, float* d_raw, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && raw && z && rays_d && d_raw && raw_ch >= 4 && ld_d >= 3,
+                "nerfb_raw2outputs_bwd: bad arguments");
+  NERFB_REQUIRE(S <= 1024, "nerfb_raw2outputs_bwd: at most 1024 samples per ray (got %d)", S);
+  if (R == 0) return NERFB_OK;
+  const size_t smem = (size_t)CW * 3 * S * sizeof(float);
+  raw2outputs_bwd_kernel<<<cdiv(R, CW), 32 * CW, smem, as_stream(stream)>>>(
+      R, S, raw, raw_ch, z, rays_d, ld_d, noise, white_bkgd, d_rgb, d_disp, d_acc, d_weights, d_depth, d_raw);
+  return check_launch("raw2outputs_bwd_kernel");
+}

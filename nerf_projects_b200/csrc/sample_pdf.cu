@@ -1,0 +1,240 @@
+// Hierarchical sampling: sample_pdf (nerf_helpers.py:372-439) and the
+// z_mid / sample / sort / z_std block of render_rays (ipynb:459-467, 486).
+// One warp per ray.  The arithmetic follows oracle/sample_pdf_np.py operation
+// by operation so that indices AND samples are bit-identical to the
+// reference's CPU fp32 result:
+//   * S = torch.sum(w) in ATen's vectorised order (8 lanes x 4 ILP slots,
+//     4-level cascade, sequential scalar tail, lanes added in order);
+//   * pdf = w / S with IEEE division; cdf = fp64 running sum rounded to fp32
+//     (all partial sums are exact in fp64, so a parallel scan is bit-safe);
+//   * u = torch.linspace formula (single-rounded fma in the upper half);
+//   * searchsorted(right=True) by binary search; un-fused fp32 lerp.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace nerfb {
+
+constexpr int PW = 4;  // warps per block
+
+__device__ __forceinline__ int ceil_log2_aten(int x) {  // c10::utils::CeilLog2
+  if (x <= 2) return 1;
+  return 32 - __clz(x - 1);
+}
+
+// ATen multi_row_sum for one (ILP slot, vector lane): items w[(4*i+k)*stride_v + l]
+__device__ __forceinline__ float cascade_sum(const float* __restrict__ w, int size_ilp, int k, int lanes, int l) {
+  const int level_power = max(4, ceil_log2_aten(size_ilp) / 4);
+  const int level_step = 1 << level_power;
+  const int level_mask = level_step - 1;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int i = 0;
+  while (i + level_step <= size_ilp) {
+    for (int j = 0; j < level_step; ++j, ++i) acc[0] = __fadd_rn(acc[0], w[(4 * i + k) * lanes + l]);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      acc[j] = __fadd_rn(acc[j], acc[j - 1]);
+      acc[j - 1] = 0.f;
+      if ((i & (level_mask << (j * level_power))) != 0) break;
+    }
+  }
+  for (; i < size_ilp; ++i) acc[0] = __fadd_rn(acc[0], w[(4 * i + k) * lanes + l]);
+#pragma unroll
+  for (int j = 1; j < 4; ++j) acc[0] = __fadd_rn(acc[0], acc[j]);
+  return acc[0];
+}
+
+// fp32 torch.sum over w[0..n) (contiguous) in ATen CPU order; result on all lanes
+__device__ float aten_sum_f32(const float* __restrict__ w, int n, int lane) {
+  float result = 0.f;
+  if (n < 8) {
+    if (lane == 0) {
+      const int size_ilp = n / 4;
+      float part[4];
+      for (int k = 0; k < 4; ++k) part[k] = cascade_sum(w, size_ilp, k, 1, 0);
+      for (int i = size_ilp * 4; i < n; ++i) part[0] = __fadd_rn(part[0], w[i]);
+      for (int k = 1; k < 4; ++k) part[0] = __fadd_rn(part[0], part[k]);
+      result = part[0];
+    }
+    return __shfl_sync(0xffffffffu, result, 0);
+  }
+  const int nvec = n / 8;
+  const int size_ilp = nvec / 4;
+  const int k = lane >> 3, l = lane & 7;
+  float part = cascade_sum(w, size_ilp, k, 8, l);
+  if (k == 0)
+    for (int v = size_ilp * 4; v < nvec; ++v) part = __fadd_rn(part, w[v * 8 + l]);
+#pragma unroll
+  for (int kk = 1; kk < 4; ++kk) {
+    const float other = __shfl_sync(0xffffffffu, part, kk * 8 + l);
+    if (k == 0) part = __fadd_rn(part, other);
+  }
+  float tail = 0.f;
+  if (lane == 0)
+    for (int j = nvec * 8; j < n; ++j) tail = __fadd_rn(tail, w[j]);
+#pragma unroll
+  for (int ll = 0; ll < 8; ++ll) {
+    const float v = __shfl_sync(0xffffffffu, part, ll);
+    if (lane == 0) tail = __fadd_rn(tail, v);
+  }
+  return __shfl_sync(0xffffffffu, tail, 0);
+}
+
+// Builds the CDF for one ray.  s_w: n = M-1 weights already offset by +1e-5;
+// writes s_cdf[0..M).
+__device__ void build_cdf(float* __restrict__ s_w, float* __restrict__ s_cdf, int M, int lane) {
+  const int n = M - 1;
+  const float S = aten_sum_f32(s_w, n, lane);
+  const int seg = (n + 31) / 32;
+  const int j0 = min(n, lane * seg), j1 = min(n, j0 + seg);
+  double local = 0.0;
+  for (int j = j0; j < j1; ++j) local += (double)__fdiv_rn(s_w[j], S);
+  double incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double q = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += q;
+  }
+  double run = incl - local;
+  if (lane == 0) s_cdf[0] = 0.f;
+  for (int j = j0; j < j1; ++j) {
+    run += (double)__fdiv_rn(s_w[j], S);
+    s_cdf[j + 1] = (float)run;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float draw_sample(const float* __restrict__ s_cdf, const float* __restrict__ s_bins,
+                                             int M, float u, int* ind_out) {
+  int lo = 0, hi = M;
+  while (lo < hi) {  // searchsorted(right=True): #{j : cdf[j] <= u}
+    const int mid = (lo + hi) >> 1;
+    if (s_cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  *ind_out = lo;
+  const int below = max(lo - 1, 0), above = min(lo, M - 1);
+  const float c0 = s_cdf[below], c1 = s_cdf[above];
+  float denom = __fsub_rn(c1, c0);
+  if (denom < 1e-5f) denom = 1.0f;
+  const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+  const float b0 = s_bins[below], b1 = s_bins[above];
+  return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+}
+
+__global__ void __launch_bounds__(32 * PW)
+sample_pdf_kernel(int R, int M, int N, const float* __restrict__ bins, int ld_bins,
+                  const float* __restrict__ weights, int ld_w, int det, const float* __restrict__ u_in,
+                  float* __restrict__ samples, long long* __restrict__ inds) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * PW + wib;
+  if (r >= R) return;
+  float* s_w = smem + (size_t)wib * 3 * M;
+  float* s_cdf = s_w + M;
+  float* s_bins = s_cdf + M;
+  for (int j = lane; j < M - 1; j += 32) s_w[j] = __fadd_rn(weights[(size_t)r * ld_w + j], 1e-5f);
+  for (int j = lane; j < M; j += 32) s_bins[j] = bins[(size_t)r * ld_bins + j];
+  __syncwarp();
+  build_cdf(s_w, s_cdf, M, lane);
+  for (int i = lane; i < N; i += 32) {
+    const float u = det ? linspace01(i, N) : u_in[(size_t)r * N + i];
+    int ind;
+    samples[(size_t)r * N + i] = draw_sample(s_cdf, s_bins, M, u, &ind);
+    if (inds) inds[(size_t)r * N + i] = ind;
+  }
+}
+
+__global__ void __launch_bounds__(32 * PW)
+hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, const float* __restrict__ weights,
+                      int det, const float* __restrict__ u_in, float* __restrict__ z_out,
+                      float* __restrict__ z_samples, long long* __restrict__ inds, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * PW + wib;
+  if (r >= R) return;
+  const int M = S - 1;  // bins = z_mid (S-1 edges), weights[1:-1] (S-2 values)
+  float* s_w = smem + (size_t)wib * (3 * M + P);
+  float* s_cdf = s_w + M;
+  float* s_bins = s_cdf + M;
+  float* s_sort = s_bins + M;
+  const float* zr = z + (size_t)r * S;
+  const float* wr = weights + (size_t)r * S;
+  for (int j = lane; j < M - 1; j += 32) s_w[j] = __fadd_rn(wr[j + 1], 1e-5f);
+  for (int j = lane; j < M; j += 32) s_bins[j] = __fmul_rn(0.5f, __fadd_rn(zr[j + 1], zr[j]));
+  for (int j = lane; j < S; j += 32) s_sort[j] = zr[j];
+  for (int j = S + N + lane; j < P; j += 32) s_sort[j] = CUDART_INF_F;
+  __syncwarp();
+  build_cdf(s_w, s_cdf, M, lane);
+  double sum = 0.0;
+  for (int i = lane; i < N; i += 32) {
+    const float u = det ? linspace01(i, N) : u_in[(size_t)r * N + i];
+    int ind;
+    const float s = draw_sample(s_cdf, s_bins, M, u, &ind);
+    s_sort[S + i] = s;
+    sum += (double)s;
+    if (z_samples) z_samples[(size_t)r * N + i] = s;
+    if (inds) inds[(size_t)r * N + i] = ind;
+  }
+  __syncwarp();
+  if (z_std) {  // torch.std(unbiased=False): population std of the N new samples
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double mean = sum / N;
+    double var = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      const double d = (double)s_sort[S + i] - mean;
+      var += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    if (lane == 0) z_std[r] = (float)sqrt(var / N);
+  }
+  // torch.sort(cat([z_vals, z_samples])): warp bitonic sort over P = pow2 >= S+N
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < P; t += 32) {
+        const int partner = t ^ j;
+        if (partner > t) {
+          const float a = s_sort[t], b = s_sort[partner];
+          const bool up = ((t & k) == 0);
+          if ((a > b) == up) { s_sort[t] = b; s_sort[partner] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int j = lane; j < S + N; j += 32) z_out[(size_t)r * (S + N) + j] = s_sort[j];
+}
+
+}  // namespace nerfb
+
+using namespace nerfb;
+
+extern "C" int nerfb_sample_pdf(int R, int M, int N, const float* bins, int ld_bins, const float* weights,
+                                int ld_w, int det, const float* u, float* samples, long long* inds,
+                                void* stream) {
+  NERFB_REQUIRE(R >= 0 && M >= 2 && N >= 1 && bins && weights && samples && ld_bins >= M && ld_w >= M - 1,
+                "nerfb_sample_pdf: bad arguments (R=%d M=%d N=%d)", R, M, N);
+  NERFB_REQUIRE(det || u, "nerfb_sample_pdf: det=0 needs u");
+  const size_t smem = (size_t)PW * 3 * M * sizeof(float);
+  NERFB_REQUIRE(smem <= 48 * 1024, "nerfb_sample_pdf: too many bins (%d)", M);
+  if (R == 0) return NERFB_OK;
+  sample_pdf_kernel<<<cdiv(R, PW), 32 * PW, smem, as_stream(stream)>>>(R, M, N, bins, ld_bins, weights, ld_w, det, u,
+                                                                      samples, inds);
+  return check_launch("sample_pdf_kernel");
+}
+
+extern "C" int nerfb_hierarchical_z(int R, int S, int N, const float* z, const float* weights, int det,
+                                    const float* u, float* z_out, float* z_samples, long long* inds,
+                                    float* z_std, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S >= 3 && N >= 1 && z && weights && z_out,
+                "nerfb_hierarchical_z: bad arguments (R=%d S=%d N=%d)", R, S, N);
+  NERFB_REQUIRE(det || u, "nerfb_hierarchical_z: det=0 needs u");
+  int P = 1;
+  while (P < S + N) P <<= 1;
+  const size_t smem = (size_t)PW * (3 * (S - 1) + P) * sizeof(float);
+  NERFB_REQUIRE(smem <= 48 * 1024, "nerfb_hierarchical_z: S+N too large (%d+%d)", S, N);
+  if (R == 0) return NERFB_OK;
+  hierarchical_z_kernel<<<cdiv(R, PW), 32 * PW, smem, as_stream(stream)>>>(R, S, N, P, z, weights, det, u, z_out,
+                                                                          z_samples, inds, z_std);
+  return check_launch("hierarchical_z_kernel");
+}

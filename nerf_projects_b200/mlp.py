@@ -1,0 +1,226 @@
+"""MLP evaluation over ray samples: run_network + NeRF.forward
+(ipynb:790-855, nerf.py:57-111) and its backward w.r.t. the parameters.
+
+Two precisions, both hand-written CUDA:
+  * ``bf16``  -- one fused tcgen05/TMEM kernel per network pass
+                 (``nerfb_mlp_fwd_bf16``), canonical 8x256 architecture only;
+  * ``fp32``  -- validation mode: encoding kernel + one SIMT SGEMM per layer,
+                 any D/W/skips.  Also provides the parameter gradients (with
+                 recompute, chunked over rays) for both modes.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+_PRECISION = os.environ.get("NERFB200_PRECISION", "bf16")
+ROWS_PER_CHUNK = 1 << 18      # rows (ray samples) processed per fp32 chunk
+
+
+def set_precision(mode: str):
+    """'bf16' (tensor cores, default) or 'fp32' (validation mode, 1e-4 parity)."""
+    global _PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def param_list(net) -> List[torch.Tensor]:
+    return list(net.parameters())
+
+
+def _enc_L(input_ch: int) -> int:
+    if input_ch == 3:
+        return -1
+    assert (input_ch - 3) % 6 == 0, f"input width {input_ch} is not 3+6L"
+    return (input_ch - 3) // 6
+
+
+# ------------------------------------------------------------------ fp32
+
+def _fwd_fp32_chunk(net, R, S, rays, z, pts, viewdirs, keep: bool):
+    """Forward of one chunk.  Returns (raw [R*S,ch], saved or None)."""
+    dev = net.pts_linears[0].weight.device
+    N = R * S
+    W, ic, icv = net.W, net.input_ch, net.input_ch_views
+    Lp = _enc_L(ic)
+    use_vd = bool(net.use_viewdirs)
+    Lv = _enc_L(icv) if use_vd else None
+    new = lambda c: torch.empty((N, c), dtype=torch.float32, device=dev)
+
+    if (net.D - 1) in net.skips:
+        raise L.NerfB200Error("a skip connection after the last pts layer is not supported "
+                              "(the reference module cannot run it either)")
+    X: List[torch.Tensor] = []            # X[i] = input buffer of pts layer i
+    catv = new(W + icv) if use_vd else None
+    x0 = new(ic)
+    ops.embed_samples(R, S, rays, z, pts, viewdirs, Lp, Lv, x0, 0, catv, W if use_vd else 0)
+    cur = x0
+    pingpong = [None, None]
+    for i, lin in enumerate(net.pts_linears):
+        if i in net.skips:
+            nxt = new(ic + W)             # [gamma(x) | h_i]  (nerf.py:79-80)
+            ops.embed_samples(R, S, rays, z, pts, None, Lp, None, nxt, 0, None, 0)
+            out = nxt[:, ic:]
+        else:
+            if keep:
+                nxt = new(W)
+            else:
+                if pingpong[i % 2] is None:
+                    pingpong[i % 2] = new(W)
+                nxt = pingpong[i % 2]
+            out = nxt
+        ops.linear_fwd(cur, lin.weight, lin.bias, out, True)
+        X.append(cur)
+        cur = nxt
+    h_last = cur
+    saved = None
+    if use_vd:
+        raw = new(4)
+        ops.linear_fwd(h_last, net.alpha_linear.weight, net.alpha_linear.bias, raw[:, 3:], False)
+        ops.linear_fwd(h_last, net.feature_linear.weight, net.feature_linear.bias, catv[:, :W], False)
+        hv = new(W // 2)
+        ops.linear_fwd(catv, net.views_linears[0].weight, net.views_linears[0].bias, hv, True)
+        ops.linear_fwd(hv, net.rgb_linear.weight, net.rgb_linear.bias, raw[:, :3], False)
+        if keep:
+            saved = dict(X=X, h_last=h_last, catv=catv, hv=hv)
+    else:
+        raw = new(net.output_ch)
+        ops.linear_fwd(h_last, net.output_linear.weight, net.output_linear.bias, raw, False)
+        if keep:
+            saved = dict(X=X, h_last=h_last)
+    return raw, saved
+
+
+def _bwd_fp32_chunk(net, saved, d_raw, grads: Dict[str, torch.Tensor]):
+    """Accumulates d loss / d params of one chunk into ``grads`` (name -> tensor)."""
+    dev = d_raw.device
+    N = d_raw.shape[0]
+    W, ic = net.W, net.input_ch
+    new = lambda c: torch.empty((N, c), dtype=torch.float32, device=dev)
+    X, h_last = saved["X"], saved["h_last"]
+    g = lambda name: grads[name]
+    if net.use_viewdirs:
+        catv, hv = saved["catv"], saved["hv"]
+        ops.linear_bwd_weight(d_raw[:, :3], hv, g("rgb_linear.weight"), g("rgb_linear.bias"))
+        d_hv = new(W // 2)
+        ops.linear_bwd_data(d_raw[:, :3], net.rgb_linear.weight, d_hv, relu_src=hv)
+        ops.linear_bwd_weight(d_hv, catv, g("views_linears.0.weight"), g("views_linears.0.bias"))
+        d_feat = new(W)
+        ops.linear_bwd_data(d_hv, net.views_linears[0].weight[:, :W], d_feat)
+        ops.linear_bwd_weight(d_feat, h_last, g("feature_linear.weight"), g("feature_linear.bias"))
+        ops.linear_bwd_weight(d_raw[:, 3:4], h_last, g("alpha_linear.weight"), g("alpha_linear.bias"))
+        d_h = new(h_last.shape[1])
+        ops.linear_bwd_data(d_feat, net.feature_linear.weight, d_h)
+        ops.linear_bwd_data(d_raw[:, 3:4], net.alpha_linear.weight, d_h, relu_src=h_last, accumulate=True)
+    else:
+        oc = net.output_ch
+        ops.linear_bwd_weight(d_raw[:, :oc], h_last, g("output_linear.weight"), g("output_linear.bias"))
+        d_h = new(h_last.shape[1])
+        ops.linear_bwd_data(d_raw[:, :oc], net.output_linear.weight, d_h, relu_src=h_last)
+    if d_h.shape[1] != W:       # skip after the last layer: keep only the h part
+        d_h = d_h[:, ic:]
+    for i in range(net.D - 1, -1, -1):
+        lin = net.pts_linears[i]
+        ops.linear_bwd_weight(d_h, X[i], g(f"pts_linears.{i}.weight"), g(f"pts_linears.{i}.bias"))
+        if i == 0:
+            break
+        off = ic if (i - 1) in net.skips else 0
+        d_prev = new(W)
+        ops.linear_bwd_data(d_h, lin.weight[:, off:], d_prev, relu_src=X[i][:, off:])
+        d_h = d_prev
+
+
+def _slice_rows(t, r0, r1, S=None):
+    if t is None:
+        return None
+    return t[r0:r1] if S is None else t[r0 * S:r1 * S]
+
+
+def forward_fp32(net, R, S, rays, z, pts=None, viewdirs=None):
+    ch = 4 if net.use_viewdirs else net.output_ch
+    dev = net.pts_linears[0].weight.device
+    step = max(1, ROWS_PER_CHUNK // S)
+    if R <= step:
+        return _fwd_fp32_chunk(net, R, S, rays, z, pts, viewdirs, keep=False)[0]
+    raw = torch.empty((R * S, ch), dtype=torch.float32, device=dev)
+    for r0 in range(0, R, step):
+        r1 = min(R, r0 + step)
+        out, _ = _fwd_fp32_chunk(net, r1 - r0, S, _slice_rows(rays, r0, r1), _slice_rows(z, r0, r1),
+                                 _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), keep=False)
+        raw[r0 * S:r1 * S].copy_(out)
+    return raw
+
+
+def backward_fp32(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.Tensor]:
+    """Parameter gradients of sum(raw * d_raw) with forward recompute per chunk."""
+    grads = {n: torch.zeros_like(p) for n, p in net.named_parameters()}
+    step = max(1, (ROWS_PER_CHUNK // 4) // S)
+    for r0 in range(0, R, step):
+        r1 = min(R, r0 + step)
+        _, saved = _fwd_fp32_chunk(net, r1 - r0, S, _slice_rows(rays, r0, r1), _slice_rows(z, r0, r1),
+                                   _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), keep=True)
+        _bwd_fp32_chunk(net, saved, d_raw[r0 * S:r1 * S], grads)
+    return grads
+
+
+# ------------------------------------------------------------------ bf16
+
+_P_INDEX = {}
+for _i in range(8):
+    _P_INDEX[f"pts_linears.{_i}.weight"] = 2 * _i
+    _P_INDEX[f"pts_linears.{_i}.bias"] = 2 * _i + 1
+for _k, _name in enumerate(["views_linears.0", "feature_linear", "alpha_linear", "rgb_linear", "output_linear"]):
+    _P_INDEX[_name + ".weight"] = 16 + 2 * _k
+    _P_INDEX[_name + ".bias"] = 17 + 2 * _k
+
+
+def packed_weights(net) -> torch.Tensor:
+    """bf16 UMMA smem images of the network, re-packed only when a parameter changed."""
+    params = dict(net.named_parameters())
+    key = tuple((p.data_ptr(), p._version) for p in params.values())
+    if net._packed is not None and net._packed_key == key:
+        return net._packed
+    dev = net.pts_linears[0].weight.device
+    nbytes = ops.packed_weights_bytes(net.use_viewdirs)
+    if net._packed is None or net._packed.numel() != nbytes or net._packed.device != dev:
+        net._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ptrs = [None] * L.NERFB_NUM_PARAMS
+    for name, p in params.items():
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            raise L.NerfB200Error(f"parameter {name} must be contiguous fp32")
+        ptrs[_P_INDEX[name]] = p.data_ptr()
+    ops.pack_weights(ptrs, net.use_viewdirs, net.output_ch, net._packed)
+    net._packed_key = key
+    return net._packed
+
+
+def forward_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
+    if not net.is_canonical():
+        raise L.NerfB200Error("the bf16 tensor-core kernel supports the canonical NeRF MLP only "
+                              "(D=8, W=256, skips=[4], multires 10/4); use set_precision('fp32')")
+    dev = net.pts_linears[0].weight.device
+    ch = 4 if net.use_viewdirs else net.output_ch
+    raw = torch.empty((R * S, ch), dtype=torch.float32, device=dev)
+    ops.mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, net.use_viewdirs, packed_weights(net), raw)
+    return raw
+
+
+def forward(net, R, S, rays, z, pts=None, viewdirs=None):
+    if _PRECISION == "bf16":
+        return forward_bf16(net, R, S, rays, z, pts, viewdirs)
+    return forward_fp32(net, R, S, rays, z, pts, viewdirs)
+
+
+def backward(net, R, S, rays, z, pts, viewdirs, d_raw):
+    # gradients are computed by the fp32 kernels in both modes (round 1)
+    return backward_fp32(net, R, S, rays, z, pts, viewdirs, d_raw)

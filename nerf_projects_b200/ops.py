@@ -1,0 +1,252 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see autograd.py).
+
+Every function takes/returns CUDA fp32 torch tensors and enqueues work on the
+current torch CUDA stream.  torch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+# launch counter: every C-ABI call that enqueues kernels bumps it by the number
+# of kernels it launches (bench.py reports it as `gpu_launches`).
+_launches = 0
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _empty(shape, like=None, device=None, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device if like is not None else device)
+
+
+# ------------------------------------------------------------------ rays
+
+def get_rays(H: int, W: int, fx, fy, cx, cy, c2w: torch.Tensor):
+    c2w = L.f32c(c2w[:3, :4])
+    L.require_cuda(c2w)
+    ro = _empty((H, W, 3), c2w)
+    rd = _empty((H, W, 3), c2w)
+    L.check(L.load().nerfb_get_rays(H, W, float(fx), float(fy), float(cx), float(cy), L.ptr(c2w), L.ptr(ro),
+                                    L.ptr(rd), L.stream()), "nerfb_get_rays")
+    _count()
+    return ro, rd
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    sh = rays_o.shape
+    o = L.f32c(rays_o).reshape(-1, 3)
+    d = L.f32c(rays_d.expand(sh) if rays_d.shape != sh else rays_d).reshape(-1, 3)
+    L.require_cuda(o, d)
+    oo, od = torch.empty_like(o), torch.empty_like(d)
+    L.check(L.load().nerfb_ndc_rays(o.shape[0], int(H), int(W), float(focal), float(near), L.ptr(o), L.ptr(d),
+                                    L.ptr(oo), L.ptr(od), L.stream()), "nerfb_ndc_rays")
+    _count()
+    return oo.reshape(sh), od.reshape(sh)
+
+
+def pack_rays(rays_o, rays_d, view_d, use_viewdirs, ndc, H, W, focal, near, far):
+    o = L.f32c(rays_o).reshape(-1, 3)
+    d = L.f32c(rays_d).reshape(-1, 3)
+    v = L.f32c(view_d).reshape(-1, 3) if use_viewdirs else None
+    L.require_cuda(o, d, v)
+    n = o.shape[0]
+    out = _empty((n, 11 if use_viewdirs else 8), o)
+    L.check(L.load().nerfb_pack_rays(n, L.ptr(o), L.ptr(d), L.ptr(v), int(bool(use_viewdirs)), int(bool(ndc)),
+                                     int(H), int(W), float(focal), float(near), float(far), L.ptr(out),
+                                     L.stream()), "nerfb_pack_rays")
+    _count()
+    return out
+
+
+def coarse_z(rays, S, lindisp=False, t_rand=None):
+    rays = L.f32c(rays)
+    L.require_cuda(rays, t_rand)
+    R = rays.shape[0]
+    z = _empty((R, S), rays)
+    if t_rand is not None:
+        t_rand = L.f32c(t_rand)
+    L.check(L.load().nerfb_coarse_z(R, int(S), L.ptr(rays), rays.shape[1], int(bool(lindisp)), L.ptr(t_rand),
+                                    L.ptr(z), L.stream()), "nerfb_coarse_z")
+    _count()
+    return z
+
+
+# ------------------------------------------------------------- encoding
+
+def enc_dim(L_: int) -> int:
+    return 3 if L_ < 0 else 3 + 6 * L_
+
+
+def embed(x, Lf: int, out=None, col0=0):
+    x2 = L.f32c(x).reshape(-1, x.shape[-1])
+    L.require_cuda(x2)
+    n = x2.shape[0]
+    if out is None:
+        out = _empty((n, enc_dim(Lf)), x2)
+    L.check(L.load().nerfb_embed(n, L.ptr(x2), x2.shape[1], int(Lf), L.ptr(out), out.shape[1], int(col0),
+                                 L.stream()), "nerfb_embed")
+    _count()
+    return out
+
+
+def embed_samples(R, S, rays, z, pts, viewdirs, Lp, Lv, enc, col_pts, enc_dir, col_dir):
+    L.check(L.load().nerfb_embed_samples(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
+                                         L.ptr(z), L.ptr(pts), L.ptr(viewdirs), int(Lp),
+                                         int(Lv) if Lv is not None else L.NERFB_NO_VIEWS, L.ptr(enc), enc.shape[1],
+                                         int(col_pts), L.ptr(enc_dir), enc_dir.shape[1] if enc_dir is not None else 0,
+                                         int(col_dir), L.stream()), "nerfb_embed_samples")
+    _count()
+
+
+# -------------------------------------------------- fp32 linear layers
+
+def _ld(t):
+    assert t.stride(-1) == 1 or t.shape[-1] == 1, "innermost dimension must be contiguous"
+    return t.stride(0) if t.dim() == 2 else t.shape[-1]
+
+
+def linear_fwd(X, W, b, Y, relu: bool, K: Optional[int] = None):
+    """Y[:, :N] = act(X[:, :K] W^T + b); X/Y may be column windows of wider buffers."""
+    M = X.shape[0]
+    N, Kw = W.shape
+    K = Kw if K is None else K
+    L.check(L.load().nerfb_linear_fwd(M, N, K, L.ptr(X), _ld(X), L.ptr(W), _ld(W), L.ptr(b), L.ptr(Y), _ld(Y),
+                                      int(relu), L.stream()), "nerfb_linear_fwd")
+    _count()
+    return Y
+
+
+def linear_bwd_data(dY, W, dX, relu_src=None, accumulate=False):
+    """dX = (dX +) dY W  (* relu_src>0).  W may be a column window W[:, a:b]."""
+    M, N = dY.shape[0], W.shape[0]
+    K = W.shape[1]
+    L.check(L.load().nerfb_linear_bwd_data(M, N, K, L.ptr(dY), _ld(dY), L.ptr(W), _ld(W), L.ptr(dX), _ld(dX),
+                                           L.ptr(relu_src), _ld(relu_src) if relu_src is not None else 0,
+                                           int(accumulate), L.stream()), "nerfb_linear_bwd_data")
+    _count()
+    return dX
+
+
+def linear_bwd_weight(dY, X, dW, db):
+    """dW += dY^T X ; db += colsum(dY).  dY may be a column window (N = dW.shape[0])."""
+    M = X.shape[0]
+    N, K = dW.shape
+    L.check(L.load().nerfb_linear_bwd_weight(M, N, K, L.ptr(dY), _ld(dY), L.ptr(X), _ld(X), L.ptr(dW), _ld(dW),
+                                             L.ptr(db), L.stream()), "nerfb_linear_bwd_weight")
+    _count(2 if db is not None else 1)
+
+
+# ---------------------------------------------------------- compositing
+
+def raw2outputs_fwd(raw, z, rays_d, noise=None, white_bkgd=False, want_weights=True):
+    R, S, ch = raw.shape
+    L.require_cuda(raw, z, rays_d, noise)
+    rgb = _empty((R, 3), raw)
+    disp = _empty((R,), raw)
+    acc = _empty((R,), raw)
+    depth = _empty((R,), raw)
+    weights = _empty((R, S), raw) if want_weights else None
+    L.check(L.load().nerfb_raw2outputs_fwd(R, S, L.ptr(raw), ch, L.ptr(z), L.ptr(rays_d), rays_d.stride(0),
+                                           L.ptr(noise), int(bool(white_bkgd)), L.ptr(rgb), L.ptr(disp), L.ptr(acc),
+                                           L.ptr(weights), L.ptr(depth), L.stream()), "nerfb_raw2outputs_fwd")
+    _count()
+    return rgb, disp, acc, weights, depth
+
+
+def raw2outputs_bwd(raw, z, rays_d, noise, white_bkgd, d_rgb, d_disp, d_acc, d_weights, d_depth):
+    R, S, ch = raw.shape
+    d_raw = torch.empty_like(raw)
+    gs = [None if g is None else L.f32c(g) for g in (d_rgb, d_disp, d_acc, d_weights, d_depth)]
+    L.check(L.load().nerfb_raw2outputs_bwd(R, S, L.ptr(raw), ch, L.ptr(z), L.ptr(rays_d), rays_d.stride(0),
+                                           L.ptr(noise), int(bool(white_bkgd)), *[L.ptr(g) for g in gs],
+                                           L.ptr(d_raw), L.stream()), "nerfb_raw2outputs_bwd")
+    _count()
+    return d_raw
+
+
+# ------------------------------------------------ hierarchical sampling
+
+def sample_pdf(bins, weights, N, det=True, u=None, want_inds=False):
+    L.require_cuda(bins, weights, u)
+    assert bins.dim() == 2 and weights.dim() == 2 and bins.stride(1) == 1 and weights.stride(1) == 1
+    R, M = bins.shape
+    samples = _empty((R, N), bins)
+    inds = _empty((R, N), bins, dtype=torch.int64) if want_inds else None
+    if u is not None:
+        u = L.f32c(u)
+    L.check(L.load().nerfb_sample_pdf(R, M, int(N), L.ptr(bins), bins.stride(0), L.ptr(weights), weights.stride(0),
+                                      int(bool(det)), L.ptr(u), L.ptr(samples), L.ptr(inds), L.stream()),
+            "nerfb_sample_pdf")
+    _count()
+    return (samples, inds) if want_inds else samples
+
+
+def hierarchical_z(z, weights, N, det=True, u=None, want_inds=False):
+    L.require_cuda(z, weights, u)
+    R, S = z.shape
+    z_out = _empty((R, S + N), z)
+    z_samples = _empty((R, N), z)
+    z_std = _empty((R,), z)
+    inds = _empty((R, N), z, dtype=torch.int64) if want_inds else None
+    if u is not None:
+        u = L.f32c(u)
+    L.check(L.load().nerfb_hierarchical_z(R, S, int(N), L.ptr(z), L.ptr(weights), int(bool(det)), L.ptr(u),
+                                          L.ptr(z_out), L.ptr(z_samples), L.ptr(inds), L.ptr(z_std), L.stream()),
+            "nerfb_hierarchical_z")
+    _count()
+    return z_out, z_samples, z_std, inds
+
+
+# ------------------------------------------------ tensor-core MLP (bf16)
+
+def packed_weights_bytes(use_viewdirs: bool) -> int:
+    return int(L.load().nerfb_packed_weights_bytes(int(bool(use_viewdirs))))
+
+
+def pack_weights(param_ptrs: Sequence[Optional[int]], use_viewdirs: bool, out_ch: int, packed: torch.Tensor):
+    arr = (C.c_void_p * L.NERFB_NUM_PARAMS)(*[p if p else None for p in param_ptrs])
+    L.check(L.load().nerfb_pack_weights(arr, int(bool(use_viewdirs)), int(out_ch), L.ptr(packed), L.stream()),
+            "nerfb_pack_weights")
+    _count()
+
+
+def mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, packed, raw):
+    L.check(L.load().nerfb_mlp_fwd_bf16(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
+                                        L.ptr(z), L.ptr(pts), L.ptr(viewdirs), int(bool(use_viewdirs)),
+                                        L.ptr(packed), L.ptr(raw), L.stream()), "nerfb_mlp_fwd_bf16")
+    _count()
+    return raw
+
+
+def umma_selftest(A, B):
+    N, K = B.shape
+    Cm = _empty((128, N), A)
+    L.check(L.load().nerfb_umma_selftest(N, K, L.ptr(A), L.ptr(B), L.ptr(Cm), L.stream()), "nerfb_umma_selftest")
+    _count()
+    return Cm
+
+
+# ------------------------------------------------------------ optimiser
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    n = len(params)
+    for i0 in range(0, n, L.NERFB_ADAM_MAX):
+        sl = slice(i0, min(n, i0 + L.NERFB_ADAM_MAX))
+        k = sl.stop - sl.start
+        mk = lambda ts: (C.c_void_p * k)(*[t.data_ptr() for t in ts[sl]])
+        numel = (C.c_longlong * k)(*[t.numel() for t in params[sl]])
+        L.check(L.load().nerfb_adam_step(k, mk(params), mk(grads), mk(exp_avg), mk(exp_avg_sq), numel, float(lr),
+                                         float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
+                                         L.stream()), "nerfb_adam_step")
+        _count()

@@ -14,10 +14,12 @@ operation:
   * ``w = weights + 1e-5``                       fp32 add            (:396)
   * ``S = torch.sum(w, -1)``                     8-lane vectorised fp32 sum:
         vectors of 8 lanes are dealt round-robin to 4 accumulators for the
-        first 4*floor(nvec/4) vectors, leftover vectors go to accumulator 0,
-        then acc0 += acc1; acc0 += acc2; acc0 += acc3 (lane-wise); then a
-        scalar tail over the n%8 trailing elements (sequential, starting from
-        0), then the 8 lanes of acc0 are added to it in lane order.   (:397)
+        first 4*floor(nvec/4) vectors (each accumulator is a 4-level cascade
+        flushed every 16 rows, which only matters for n >= 512), leftover
+        vectors go to accumulator 0, then acc0 += acc1; acc0 += acc2;
+        acc0 += acc3 (lane-wise); then a scalar tail over the n%8 trailing
+        elements (sequential, starting from 0), then the 8 lanes of acc0 are
+        added to it in lane order.  n < 8 takes the scalar 4-slot path. (:397)
   * ``pdf = w / S``                              IEEE fp32 division  (:397)
   * ``cdf = cumsum(pdf)``                        fp64 running sum, each prefix
         rounded to fp32 on output; cdf = [0, ...]                    (:398-399)
@@ -40,39 +42,67 @@ import numpy as np
 f32 = np.float32
 
 
+def _ceil_log2(x: int) -> int:
+    return 0 if x <= 1 else int(x - 1).bit_length()
+
+
+def _multi_row_sum(items: np.ndarray, k: int, size_ilp: int) -> np.ndarray:
+    """ATen ``multi_row_sum`` (aten/src/ATen/native/cpu/SumKernel.cpp) for ILP
+    slot ``k``: rows i = 0..size_ilp-1 contribute items[..., 4*i+k, :] to a
+    4-level cascade whose level 0 is flushed upwards every ``level_step`` rows."""
+    levels = 4
+    level_power = max(4, _ceil_log2(size_ilp) // levels)
+    level_step = 1 << level_power
+    level_mask = level_step - 1
+    lead = items.shape[:-2] + items.shape[-1:]
+    acc = [np.zeros(lead, f32) for _ in range(levels)]
+    i = 0
+    while i + level_step <= size_ilp:
+        for _ in range(level_step):
+            acc[0] = (acc[0] + items[..., 4 * i + k, :]).astype(f32)
+            i += 1
+        for j in range(1, levels):
+            acc[j] = (acc[j] + acc[j - 1]).astype(f32)
+            acc[j - 1] = np.zeros(lead, f32)
+            if (i & (level_mask << (j * level_power))) != 0:
+                break
+    while i < size_ilp:
+        acc[0] = (acc[0] + items[..., 4 * i + k, :]).astype(f32)
+        i += 1
+    for j in range(1, levels):
+        acc[0] = (acc[0] + acc[j]).astype(f32)
+    return acc[0]
+
+
+def _row_sum(items: np.ndarray) -> np.ndarray:
+    """ATen ``row_sum`` with ilp_factor 4 over items[..., size, lanes]."""
+    size = items.shape[-2]
+    size_ilp = size // 4
+    part = [_multi_row_sum(items, k, size_ilp) for k in range(4)]
+    for i in range(size_ilp * 4, size):
+        part[0] = (part[0] + items[..., i, :]).astype(f32)
+    for k in range(1, 4):
+        part[0] = (part[0] + part[k]).astype(f32)
+    return part[0]
+
+
 def torch_sum_lastdim_f32(w: np.ndarray) -> np.ndarray:
-    """fp32 sum over the last axis in ATen's CPU vectorised order."""
+    """fp32 ``torch.sum(w, -1)`` of a contiguous tensor in ATen's CPU order:
+    n >= 8 -> 8-lane vectorised ``row_sum`` over the n//8 whole vectors, then a
+    sequential scalar tail starting from 0, then the 8 lanes added in order;
+    n < 8 -> scalar ``row_sum`` (4 ILP slots)."""
     w = np.ascontiguousarray(w, dtype=f32)
     n = w.shape[-1]
     lead = w.shape[:-1]
+    if n < 8:
+        return _row_sum(w[..., :, None])[..., 0]
     nvec = n // 8
-    if nvec == 0:
-        acc = np.zeros(lead, f32)
-        for j in range(n):
-            acc = (acc + w[..., j]).astype(f32)
-        return acc
-    vecs = w[..., :nvec * 8].reshape(lead + (nvec, 8))
-    full = (nvec // 4) * 4
-    accs = [None] * 4
-    if full > 0:
-        for a in range(4):
-            accs[a] = vecs[..., a, :].copy()
-        for v in range(4, full):
-            accs[v % 4] = (accs[v % 4] + vecs[..., v, :]).astype(f32)
-        start = full
-    else:
-        accs[0] = vecs[..., 0, :].copy()
-        start = 1
-    for v in range(start, nvec):
-        accs[0] = (accs[0] + vecs[..., v, :]).astype(f32)
-    if full > 0:
-        for a in range(1, 4):
-            accs[0] = (accs[0] + accs[a]).astype(f32)
+    vec_acc = _row_sum(w[..., :nvec * 8].reshape(lead + (nvec, 8)))
     tail = np.zeros(lead, f32)
     for j in range(nvec * 8, n):
         tail = (tail + w[..., j]).astype(f32)
     for lane in range(8):
-        tail = (tail + accs[0][..., lane]).astype(f32)
+        tail = (tail + vec_acc[..., lane]).astype(f32)
     return tail
 
 
