@@ -173,10 +173,16 @@ int nerfb_pack_weights(const float* const* h_params, int use_viewdirs, int out_c
 int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const float* z,
                        const float* pts, const float* viewdirs, int use_viewdirs,
                        const void* packed, float* raw, void* stream);
-/* Self-test of the tcgen05 building blocks (descriptor/swizzle/TMEM layout):
- * C[128,N] = A[128,K] B[N,K]^T with bf16-rounded inputs, K multiple of 64,
- * N multiple of 16 <= 256.  Used by tests only. */
-int nerfb_umma_selftest(int N, int K, const float* A, const float* B, float* C, void* stream);
+/* Self-test of the tcgen05 building blocks (smem descriptors, 128B swizzle,
+ * instruction descriptor, TMEM load layout, 2-CTA pairing):
+ * C[M,N] = A[M,K] B[N,K]^T with bf16-rounded inputs and fp32 accumulation,
+ * M = 128*cta_group (cta_group 1 or 2), K multiple of 64 (<= 256), N multiple
+ * of 32 (<= 256).  Used by tests only. */
+int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float* B, float* C,
+                        void* stream);
+/* Host pointer to the 8 x u64 watchdog record the tensor-core kernels write
+ * before trapping when a barrier wait times out ([0]=0xDEAD when fired). */
+const unsigned long long* nerfb_watchdog_record(void);
 
 /* ------------------------------------------------------------- optimiser */
 

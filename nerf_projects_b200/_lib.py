@@ -39,7 +39,8 @@ _SIGS = {
     "nerfb_packed_weights_bytes": ([_i], C.c_size_t),
     "nerfb_pack_weights": ([C.POINTER(_vp), _i, _i, _vp, _vp], _i),
     "nerfb_mlp_fwd_bf16": ([_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
-    "nerfb_umma_selftest": ([_i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_umma_selftest": ([_i, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_watchdog_record": ([], C.POINTER(C.c_ulonglong)),
     "nerfb_adam_step": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll),
                          _f, _f, _f, _f, _i, _f, _vp], _i),
 }
@@ -79,6 +80,14 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().nerfb_last_error().decode(errors="replace")
         raise NerfB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def watchdog_record():
+    """Decoded watchdog record of the tensor-core kernels (None if it never fired)."""
+    rec = load().nerfb_watchdog_record()
+    if not rec or rec[0] != 0xDEAD:
+        return None
+    return dict(block=rec[1] >> 32, thread=rec[1] & 0xFFFFFFFF, tag=rec[2], bar=rec[3] >> 32, parity=rec[3] & 0xFFFFFFFF)
 
 
 def ptr(t):

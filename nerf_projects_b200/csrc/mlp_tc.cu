@@ -10,7 +10,3 @@ extern "C" int nerfb_mlp_fwd_bf16(int, int, const float*, int, const float*, con
   nerfb::set_error("bf16 tensor-core path not built yet");
   return NERFB_ERR_ARG;
 }
-extern "C" int nerfb_umma_selftest(int, int, const float*, const float*, float*, void*) {
-  nerfb::set_error("bf16 tensor-core path not built yet");
-  return NERFB_ERR_ARG;
-}

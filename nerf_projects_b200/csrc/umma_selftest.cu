@@ -1,0 +1,140 @@
+// Self-test of the tcgen05 building blocks in tc05.cuh: one (cta_group 1) or
+// two paired (cta_group 2) CTAs compute C = A B^T from operands written to
+// shared memory by ordinary threads in the UMMA K-major/128B-swizzle layout --
+// exactly what the fused MLP kernel's epilogue does for its activations.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace nerfb {
+using namespace tc05;
+
+static unsigned long long* g_watch_host = nullptr;
+static unsigned long long* g_watch_dev = nullptr;
+
+tc05::Watch get_watch() {
+  if (g_watch_host == nullptr) {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 8 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+      g_watch_host = (unsigned long long*)h;
+      for (int i = 0; i < 8; ++i) g_watch_host[i] = 0;
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) g_watch_dev = (unsigned long long*)d;
+    }
+    cudaGetLastError();
+  }
+  tc05::Watch w;
+  w.rec = g_watch_dev;
+  return w;
+}
+
+// writes a [rows x K] fp32 matrix (row stride ld) as K/64 swizzled bf16 chunks
+__device__ void stage_operand(uint8_t* smem, const float* __restrict__ src, int rows, int K, int ld, int tid,
+                              int nthreads) {
+  const int units_per_row = K / 8;  // 16-byte units (8 bf16)
+  for (int idx = tid; idx < rows * units_per_row; idx += nthreads) {
+    const int r = idx / units_per_row, u = idx % units_per_row;
+    const float* s = src + (size_t)r * ld + u * 8;
+    uint4 v;
+    v.x = pack_bf16x2(s[0], s[1]); v.y = pack_bf16x2(s[2], s[3]);
+    v.z = pack_bf16x2(s[4], s[5]); v.w = pack_bf16x2(s[6], s[7]);
+    const int chunk = u / 8, unit = u % 8;
+    *reinterpret_cast<uint4*>(smem + (size_t)chunk * rows * 128 + sw128_offset(r, unit)) = v;
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                     Watch watch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0;
+  const int nb_rows = N / CG;                     // rows of B held by this CTA
+  uint8_t* sA = smem;                             // K/64 chunks x 16 KB
+  uint8_t* sB = smem + (size_t)(K / 64) * 128 * 128;
+
+  stage_operand(sA, A + (size_t)rank * 128 * K, 128, K, K, tid, 128);
+  stage_operand(sB, B + (size_t)rank * nb_rows * K, nb_rows, K, K, tid, 128);
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_done), 1);
+    fence_barrier_init();
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) {
+    tmem_alloc<CG>(smem_u32(&tmem_base_slot), ncols);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128 * CG, N);
+    for (int kc = 0; kc < K / 64; ++kc) {
+      const uint64_t da = make_sdesc_sw128(smem_u32(sA + (size_t)kc * 128 * 128));
+      const uint64_t db = make_sdesc_sw128(smem_u32(sB + (size_t)kc * nb_rows * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16<CG>(tmem_base, sdesc_advance_k(da, k), sdesc_advance_k(db, k), idesc, (kc | k) ? 1u : 0u);
+    }
+    umma_commit<CG>(smem_u32(&bar_done));
+  }
+  mbar_wait(smem_u32(&bar_done), 0, watch, 1);
+  tc_fence_after();
+  const int row = warp * 32 + (tid & 31);
+  float* crow = C + ((size_t)rank * 128 + row) * N;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) crow[c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) tmem_dealloc<CG>(tmem_base, ncols);
+}
+
+}  // namespace nerfb
+
+using namespace nerfb;
+
+extern "C" const unsigned long long* nerfb_watchdog_record(void) {
+  get_watch();
+  return g_watch_host;
+}
+
+extern "C" int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float* B, float* C,
+                                   void* stream) {
+  NERFB_REQUIRE((cta_group == 1 || cta_group == 2) && N >= 32 && N <= 256 && N % 32 == 0 && K >= 64 && K <= 256 &&
+                    K % 64 == 0 && A && B && C,
+                "nerfb_umma_selftest: bad arguments (cta_group=%d N=%d K=%d)", cta_group, N, K);
+  const size_t smem = (size_t)(K / 64) * 128 * 128 + (size_t)(K / 64) * (N / cta_group) * 128 + 1024;
+  tc05::Watch w = get_watch();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cta_group);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cta_group == 1) {
+    NERFB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, umma_selftest_kernel<1>, N, K, A, B, C, w));
+  } else {
+    NERFB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, umma_selftest_kernel<2>, N, K, A, B, C, w));
+  }
+  return check_launch("umma_selftest_kernel");
+}

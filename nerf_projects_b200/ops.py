@@ -229,10 +229,12 @@ def mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, packed, raw):
     return raw
 
 
-def umma_selftest(A, B):
+def umma_selftest(A, B, cta_group=1):
     N, K = B.shape
-    Cm = _empty((128, N), A)
-    L.check(L.load().nerfb_umma_selftest(N, K, L.ptr(A), L.ptr(B), L.ptr(Cm), L.stream()), "nerfb_umma_selftest")
+    assert A.shape == (128 * cta_group, K)
+    Cm = _empty((128 * cta_group, N), A)
+    L.check(L.load().nerfb_umma_selftest(int(cta_group), N, K, L.ptr(A), L.ptr(B), L.ptr(Cm), L.stream()),
+            "nerfb_umma_selftest")
     _count()
     return Cm
 
