@@ -169,9 +169,10 @@ int nerfb_pack_weights(const float* const* h_params, int use_viewdirs, int out_c
  * (bf16 operands, fp32 TMEM accumulators, fp32 density head), activations
  * never leave the SM.  Sample positions are o + d z from `rays`/`z`, or the
  * explicit `pts` ([R*S,3]) when not NULL; `viewdirs` as in nerfb_embed_samples.
- * raw: [R*S, 4] = [rgb logits, sigma]. */
+ * raw: [R*S, 4] = [rgb logits, sigma] with view directions, else [R*S, out_ch]
+ * (output_linear, out_ch = 4 or 5). */
 int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const float* z,
-                       const float* pts, const float* viewdirs, int use_viewdirs,
+                       const float* pts, const float* viewdirs, int use_viewdirs, int out_ch,
                        const void* packed, float* raw, void* stream);
 /* Self-test of the tcgen05 building blocks (smem descriptors, 128B swizzle,
  * instruction descriptor, TMEM load layout, 2-CTA pairing):

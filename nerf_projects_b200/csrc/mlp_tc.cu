@@ -1,12 +1,631 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Fused NeRF MLP forward on tcgen05 tensor cores (sm_100a).
+//
+// Replaces run_network + NeRF.forward (ipynb:790-855, nerf.py:57-111) for all
+// R*S ray samples of a chunk: sample positions o + d*z, the sin/cos positional
+// encoding (in registers), the 8x256 skip-connected MLP, the density head, the
+// feature / view-dependent layers and the rgb head run inside ONE persistent
+// kernel; activations live in shared memory (bf16) and TMEM (fp32
+// accumulators) and never touch HBM.  Output: raw[R*S, 4] = [rgb logits, sigma].
+//
+// Design (DESIGN.md section 4 has the full derivation):
+//   * one 2-CTA cluster per SM pair, tcgen05.mma.cta_group::2 (UMMA M=256,
+//     N=256, K=16): each CTA owns 128 rows (samples) of A and HALF of the weight
+//     rows of B, so a whole 256x256 layer is 64 KB per CTA and stays resident
+//     in a 4-slot ring while BOTH row tiles (A,B) of the CTA pass over it:
+//     every weight byte read from L2 feeds 512 samples;
+//   * two row tiles per CTA ping-pong: while the tensor core runs layer l of
+//     tile B, the 8 epilogue warps drain tile A's accumulator from TMEM
+//     (bias, ReLU, bf16, 128B-swizzled store = next layer's A operand);
+//   * weights are pre-packed (nerfb_pack_weights) as the exact shared-memory
+//     images (K-major, SWIZZLE_128B) and streamed with 1-D bulk async copies
+//     (cp.async.bulk, TMA engine) signalled on mbarriers;
+//   * the density head is evaluated in fp32 from the un-rounded layer-7
+//     accumulators, the rgb head in fp32 from the fp32 view
+//     layer activations;
+//   * every barrier wait is bounded by a watchdog (tc05.cuh).
 #include "common.cuh"
-extern "C" size_t nerfb_packed_weights_bytes(int) { return 16; }
-extern "C" int nerfb_pack_weights(const float* const*, int, int, void*, void*) {
-  nerfb::set_error("bf16 tensor-core path not built yet");
-  return NERFB_ERR_ARG;
+#include "tc05.cuh"
+
+namespace nerfb {
+using namespace tc05;
+
+tc05::Watch get_watch();  // umma_selftest.cu
+
+// ------------------------------------------------------------ geometry
+constexpr int kTileRows = 128;                 // rows per CTA per tile (UMMA M / 2)
+constexpr int kSuperRows = 512;                // rows per cluster per iteration (2 CTAs x 2 tiles)
+constexpr int kChunkBytes = 16384;             // 128 rows x 64 bf16 (one K chunk of A, or half of a B chunk)
+constexpr int kNS = 4;                         // weight ring slots (= one 256x256 layer per CTA)
+constexpr int kThreads = 384;                  // warps: 0 loader, 1 mma, 2 tmem, 3 relay, 4..11 epilogue
+constexpr int kEpiThreads = 256;
+
+// packed weight blob: bf16 chunk images, then the fp32 parameter block
+constexpr int kChunkFull = 2 * kChunkBytes;    // N=256 chunk: two CTA halves
+constexpr int kChunkViews = kChunkBytes;       // N=128 chunk: two halves of 64 rows
+constexpr int kNumFullChunks = 34;             // L0(1) L1-4(16) L5(1+4) L6-7(8) FEAT(4)
+constexpr int kNumViewChunks = 5;              // gamma(d) part + 4 feature parts
+constexpr int kChunkAreaVD = kNumFullChunks * kChunkFull + kNumViewChunks * kChunkViews;
+constexpr int kChunkAreaNoVD = 30 * kChunkFull;
+
+// fp32 parameter block (floats)
+constexpr int kOffBias = 0;                    // 8 x 256 pts biases
+constexpr int kOffBiasFeat = 2048;             // 256
+constexpr int kOffBiasViews = 2304;            // 128
+constexpr int kOffHeadW = 2432;                // 5 x 256: alpha_linear.weight (row 0) or output_linear.weight
+constexpr int kOffRgbW = 3712;                 // 3 x 128
+constexpr int kOffHeadB = 4096;                // 8
+constexpr int kOffRgbB = 4104;                 // 4
+constexpr int kParamFloats = 4108;
+constexpr int kParamBytes = kParamFloats * 4;  // 16432
+
+// shared memory map (bytes from the 1024-aligned dynamic smem base)
+constexpr int kSmAct = 0;                      // 2 tiles x 4 chunks
+constexpr int kSmEnc = 2 * 4 * kChunkBytes;    // 131072: gamma(x) / gamma(d) operand chunk
+constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
+constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
+constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
+constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
+constexpr int kNumBars = 3 * kNS + 2 + 2 + 1;           // w_full, w_peer, w_empty, act_ready[2], mma_done[2], enc_free
+constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
+constexpr int kSmemBytes = kSmTmemSlot + 16;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+
+// ------------------------------------------------------------- schedule
+// A static program shared by the three asynchronous roles.  Generated on the
+// host (build_schedule) and passed by value.
+struct LoadEnt { uint32_t off; uint32_t bytes; };          // blob offset of the chunk, bytes per CTA
+enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16 };
+struct OpEnt { uint8_t load, tile, asrc, flags; };          // asrc 0..3 = act chunk, 4 = enc
+struct Sched {
+  int nloads, nops, nlayers;
+  LoadEnt loads[44];
+  OpEnt ops[84];
+};
+
+static void build_schedule(bool vd, Sched& s) {
+  s.nloads = s.nops = 0;
+  s.nlayers = vd ? 10 : 8;
+  auto chunk_off = [](int id) -> uint32_t {
+    return id < kNumFullChunks ? (uint32_t)id * kChunkFull
+                               : (uint32_t)kNumFullChunks * kChunkFull + (uint32_t)(id - kNumFullChunks) * kChunkViews;
+  };
+  auto add_load = [&](int id, bool n128) -> uint8_t {
+    s.loads[s.nloads] = LoadEnt{chunk_off(id), (uint32_t)(n128 ? kChunkBytes / 2 : kChunkBytes)};
+    return (uint8_t)s.nloads++;
+  };
+  auto add_op = [&](uint8_t load, int tile, int asrc, int flags) {
+    s.ops[s.nops++] = OpEnt{load, (uint8_t)tile, (uint8_t)asrc, (uint8_t)flags};
+  };
+  // plain K=256 layer: chunks id0..id0+3, both tiles pass over the resident layer
+  auto plain = [&](int id0, bool n128) {
+    uint8_t l[4];
+    for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
+    const int f = n128 ? F_N128 : 0;
+    for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
+  };
+  // layer with an extra K=64 chunk read from the enc buffer (skip concat / view concat):
+  // tile A consumes it first, tile B last, so the 4-slot ring never needs 5 live chunks.
+  auto with_enc = [&](int id_enc, int id0, bool n128) {
+    const int f = n128 ? F_N128 : 0;
+    const uint8_t g = add_load(id_enc, n128);
+    uint8_t l[4];
+    for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
+    const uint8_t g2 = add_load(id_enc, n128);
+    add_op(g, 0, 4, f | F_FIRST | F_REL_SLOT | F_REL_ENC);
+    for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 3 ? F_LAST : 0));
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0));
+    add_op(g2, 1, 4, f | F_LAST | F_REL_SLOT | F_REL_ENC);
+  };
+  {  // layer 0: K = 64 (gamma(x)), one chunk used by both tiles
+    const uint8_t g0 = add_load(0, false);
+    add_op(g0, 0, 4, F_FIRST | F_LAST | F_REL_ENC);
+    add_op(g0, 1, 4, F_FIRST | F_LAST | F_REL_ENC | F_REL_SLOT);
+  }
+  for (int l = 1; l <= 4; ++l) plain(1 + 4 * (l - 1), false);
+  with_enc(17, 18, false);          // layer 5: [gamma(x) | h4]
+  plain(22, false);                 // layer 6
+  plain(26, false);                 // layer 7
+  if (vd) {
+    plain(30, false);               // feature_linear
+    with_enc(34, 35, true);         // views_linears[0]: [feature | gamma(d)], N = 128
+  }
 }
-extern "C" int nerfb_mlp_fwd_bf16(int, int, const float*, int, const float*, const float*, const float*, int,
-                                  const void*, float*, void*) {
-  nerfb::set_error("bf16 tensor-core path not built yet");
-  return NERFB_ERR_ARG;
+
+struct MlpArgs {
+  const float* rays; int rw;
+  const float* z; const float* pts; const float* viewdirs;
+  int S; long long nrows; int use_viewdirs; int out_ch;
+  const uint8_t* packed; float* raw;
+  int nst, nclusters;
+  Watch watch;
+};
+
+// ------------------------------------------------------------- encoding
+// value of column c of gamma(p) (embedder.py:54-65): [p | sin f0 p | cos f0 p | sin f1 p | ...]
+// p*2^k is reduced to revolutions with a two-term 1/2pi so the MUFU argument is
+// accurate to ~1e-7 even at 2^9 * |p| ~ 3000 rad.
+template <int L, int HH>
+__device__ __forceinline__ void encode_cols(const float (&p)[3], uint32_t (&packed)[16]) {
+  constexpr float kInv2PiHi = 0.15915494f, kInv2PiLo = 6.4206383e-09f, k2Pi = 6.2831855f;
+  float thi[3], tlo[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    thi[j] = p[j] * kInv2PiHi;
+    tlo[j] = fmaf(p[j], kInv2PiHi, -thi[j]) + p[j] * kInv2PiLo;
+  }
+  float e[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = 32 * HH + i;
+    if (c < 3) {
+      e[i] = p[c];
+    } else if (c < 3 + 6 * L) {
+      const int k = (c - 3) / 6, r = (c - 3) % 6, j = r % 3;
+      const float sc = (float)(1 << k);
+      const float a = thi[j] * sc;
+      const float f = (a - rintf(a)) + tlo[j] * sc;
+      e[i] = (r < 3) ? __sinf(f * k2Pi) : __cosf(f * k2Pi);
+    } else {
+      e[i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+}
+
+__device__ __forceinline__ void store_row32(uint8_t* chunk, int row, int unit0, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint4*>(chunk + sw128_offset(row, unit0 + i)) =
+        make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+// -------------------------------------------------------------- kernel
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const uint32_t sbase = smem_u32(smem);
+
+  float* s_par = reinterpret_cast<float*>(smem + kSmParams);
+  float* s_sig = reinterpret_cast<float*>(smem + kSmSig);
+  auto bar = [&](int i) -> uint32_t { return sbase + kSmBars + 8 * i; };
+  const int B_FULL = 0, B_PEER = kNS, B_EMPTY = 2 * kNS, B_ACT = 3 * kNS, B_DONE = 3 * kNS + 2, B_ENC = 3 * kNS + 4;
+
+  if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xA11, sbase, 0);
+
+  // ---- one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(bar(B_FULL + s), 1);
+      mbar_init(bar(B_PEER + s), 1);
+      mbar_init(bar(B_EMPTY + s), 1);
+    }
+    mbar_init(bar(B_ACT + 0), 2);
+    mbar_init(bar(B_ACT + 1), 2);
+    mbar_init(bar(B_DONE + 0), 1);
+    mbar_init(bar(B_DONE + 1), 1);
+    mbar_init(bar(B_ENC), 1);
+    fence_barrier_init();
+  }
+  {
+    const float* gpar = reinterpret_cast<const float*>(a.packed + (a.use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD));
+    for (int i = tid; i < kParamFloats; i += kThreads) s_par[i] = __ldg(gpar + i);
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(sbase + kSmTmemSlot, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kSmTmemSlot);
+
+  const int niter = (a.nst - cluster_id + a.nclusters - 1) / a.nclusters;   // super-tiles of this cluster
+
+  if (warp == 0) {
+    // ===================== weight loader (both CTAs: own half of every chunk)
+    if (lane == 0) {
+      long long gl = 0;
+      for (int it = 0; it < niter; ++it) {
+        for (int q = 0; q < sc.nloads; ++q, ++gl) {
+          const int slot = (int)(gl % kNS);
+          if (gl >= kNS) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((gl / kNS) + 1) & 1), a.watch, 0x100 + q);
+          const LoadEnt le = sc.loads[q];
+          mbar_arrive_expect_tx(bar(B_FULL + slot), le.bytes);
+          bulk_g2s(sbase + kSmRing + slot * kChunkBytes, a.packed + le.off + (size_t)rank * le.bytes, le.bytes,
+                   bar(B_FULL + slot));
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== relay (peer CTA): tell the leader my half has landed
+    if (lane == 0 && rank == 1) {
+      long long gl = 0;
+      for (int it = 0; it < niter; ++it) {
+        for (int q = 0; q < sc.nloads; ++q, ++gl) {
+          const int slot = (int)(gl % kNS);
+          mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x200 + q);
+          mbar_arrive_cluster(bar(B_PEER + slot), 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc256 = make_idesc_bf16(256, 256), idesc128 = make_idesc_bf16(256, 128);
+      uint32_t act_cnt[2] = {0, 0};
+      for (int it = 0; it < niter; ++it) {
+        const long long gl0 = (long long)it * sc.nloads;
+        for (int o = 0; o < sc.nops; ++o) {
+          const OpEnt op = sc.ops[o];
+          const long long gl = gl0 + op.load;
+          const int slot = (int)(gl % kNS);
+          const uint32_t par = (uint32_t)((gl / kNS) & 1);
+          if (op.flags & F_FIRST) {
+            mbar_wait(bar(B_ACT + op.tile), act_cnt[op.tile] & 1, a.watch, 0x300 + o);
+            act_cnt[op.tile]++;
+          }
+          mbar_wait(bar(B_FULL + slot), par, a.watch, 0x400 + o);
+          mbar_wait(bar(B_PEER + slot), par, a.watch, 0x500 + o);
+          tc_fence_after();
+          const uint32_t a_addr = (op.asrc < 4) ? (sbase + kSmAct + (op.tile * 4 + op.asrc) * kChunkBytes)
+                                                : (sbase + kSmEnc);
+          const uint64_t da = make_sdesc_sw128(a_addr);
+          const uint64_t db = make_sdesc_sw128(sbase + kSmRing + slot * kChunkBytes);
+          const uint32_t d_tmem = tmem_base + op.tile * 256;
+          const uint32_t idesc = (op.flags & F_N128) ? idesc128 : idesc256;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16<2>(d_tmem, sdesc_advance_k(da, k), sdesc_advance_k(db, k), idesc,
+                         ((op.flags & F_FIRST) && k == 0) ? 0u : 1u);
+          if (op.flags & F_REL_SLOT) umma_commit<2>(bar(B_EMPTY + slot));
+          if (op.flags & F_REL_ENC) umma_commit<2>(bar(B_ENC));
+          if (op.flags & F_LAST) umma_commit<2>(bar(B_DONE + op.tile));
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue / encoding warps
+    const int et = tid - 128;
+    const int q = warp & 3, hh = (warp - 4) >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    uint32_t done_cnt[2] = {0, 0};
+    uint32_t enc_cnt = 0;
+    const bool vd = a.use_viewdirs != 0;
+
+    auto enc_wait = [&]() {
+      if (enc_cnt > 0) mbar_wait(bar(B_ENC), (enc_cnt - 1) & 1, a.watch, 0x600 + enc_cnt);
+      ++enc_cnt;
+    };
+    auto signal_ready = [&](int t) {
+      tc_fence_before();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) mbar_arrive_cluster(bar(B_ACT + t), 0);
+    };
+    // sample position of my row in tile t
+    auto load_point = [&](long long grow, float (&p)[3]) {
+      p[0] = p[1] = p[2] = 0.f;
+      if (grow < a.nrows) {
+        if (a.pts != nullptr) {
+          p[0] = __ldg(a.pts + grow * 3 + 0); p[1] = __ldg(a.pts + grow * 3 + 1); p[2] = __ldg(a.pts + grow * 3 + 2);
+        } else {
+          const long long r = grow / a.S;
+          const float* ray = a.rays + r * a.rw;
+          const float zz = __ldg(a.z + grow);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) p[j] = __fadd_rn(__ldg(ray + j), __fmul_rn(__ldg(ray + 3 + j), zz));
+        }
+      }
+    };
+    auto load_dir = [&](long long grow, float (&p)[3]) {
+      p[0] = p[1] = p[2] = 0.f;
+      if (grow < a.nrows) {
+        const long long r = grow / a.S;
+        const float* src = a.viewdirs != nullptr ? a.viewdirs + r * 3 : a.rays + r * a.rw + 8;
+        p[0] = __ldg(src); p[1] = __ldg(src + 1); p[2] = __ldg(src + 2);
+      }
+    };
+    auto write_enc_x = [&](long long grow) {
+      float p[3];
+      load_point(grow, p);
+      uint32_t w[16];
+      if (hh == 0) encode_cols<10, 0>(p, w); else encode_cols<10, 1>(p, w);
+      store_row32(smem + kSmEnc, row, 4 * hh, w);
+    };
+    auto write_enc_d = [&](long long grow) {
+      float p[3];
+      load_dir(grow, p);
+      uint32_t w[16];
+      if (hh == 0) encode_cols<4, 0>(p, w); else encode_cols<4, 1>(p, w);
+      store_row32(smem + kSmEnc, row, 4 * hh, w);
+    };
+
+    for (int it = 0; it < niter; ++it) {
+      const long long st = cluster_id + (long long)it * a.nclusters;
+      long long grow[2];
+      grow[0] = st * kSuperRows + rank * kTileRows + row;
+      grow[1] = grow[0] + 2 * kTileRows;
+      for (int t = 0; t < 2; ++t) {       // layer-0 operands
+        enc_wait();
+        write_enc_x(grow[t]);
+        signal_ready(t);
+      }
+      for (int l = 0; l < sc.nlayers; ++l) {
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + l * 2 + t);
+          done_cnt[t]++;
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_addr + t * 256;
+          if (l <= 8 && !(l == 7 && !vd)) {
+            // ---- hidden layer: bias (+ReLU) -> bf16 -> next A operand; layer 7 also feeds the density head
+            const float* bias = s_par + (l < 8 ? kOffBias + 256 * l : kOffBiasFeat) + 128 * hh;
+            const float* hw = s_par + kOffHeadW + 128 * hh;
+            uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
+            float sig = 0.f;
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+              uint32_t v[32];
+              tmem_ld32(taddr + 128 * hh + 32 * b, v);
+              tmem_ld_wait();
+              float x[32];
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias + 32 * b + 4 * j4);
+                x[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + bb.x;
+                x[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+                x[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + bb.z;
+                x[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+              }
+              if (l != 8) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+              }
+              if (l == 7) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 ww = *reinterpret_cast<const float4*>(hw + 32 * b + 4 * j4);
+                  sig = fmaf(x[4 * j4 + 0], ww.x, sig); sig = fmaf(x[4 * j4 + 1], ww.y, sig);
+                  sig = fmaf(x[4 * j4 + 2], ww.z, sig); sig = fmaf(x[4 * j4 + 3], ww.w, sig);
+                }
+              }
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+              const int col0 = 128 * hh + 32 * b;
+              store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+            }
+            if (l == 7) s_sig[(t * 2 + hh) * 128 + row] = sig;
+          } else if (l == 7) {
+            // ---- no view directions: output_linear (out_ch x 256) in fp32 from layer-7 accumulators
+            float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            const float* bias = s_par + kOffBias + 256 * 7 + 128 * hh;
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+              uint32_t v[32];
+              tmem_ld32(taddr + 128 * hh + 32 * b, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = fmaxf(__uint_as_float(v[j]) + bias[32 * b + j], 0.f);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) part[k] = fmaf(x, s_par[kOffHeadW + 256 * k + 128 * hh + 32 * b + j], part[k]);
+              }
+            }
+            // exchange the two column halves through the (idle) enc buffer: [tile][half][row][8]
+            float* xch = reinterpret_cast<float*>(smem + kSmEnc);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) xch[((t * 2 + hh) * 128 + row) * 8 + k] = part[k];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (hh == 0 && grow[t] < a.nrows) {
+              for (int k = 0; k < a.out_ch; ++k)
+                a.raw[grow[t] * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
+                                                xch[((t * 2 + 1) * 128 + row) * 8 + k] + s_par[kOffHeadB + k];
+            }
+          } else {
+            // ---- l == 9: view layer epilogue + rgb head -> raw (one warp quarter per 32 rows)
+            if (hh == 0) {
+              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+              const float* bias = s_par + kOffBiasViews;
+              const float* rw = s_par + kOffRgbW;
+#pragma unroll 1
+              for (int b = 0; b < 4; ++b) {
+                uint32_t v[32];
+                tmem_ld32(taddr + 32 * b, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float x = fmaxf(__uint_as_float(v[j]) + bias[32 * b + j], 0.f);
+                  c0 = fmaf(x, rw[32 * b + j], c0);
+                  c1 = fmaf(x, rw[128 + 32 * b + j], c1);
+                  c2 = fmaf(x, rw[256 + 32 * b + j], c2);
+                }
+              }
+              if (grow[t] < a.nrows) {
+                const float sigma = s_sig[(t * 2 + 0) * 128 + row] + s_sig[(t * 2 + 1) * 128 + row] + s_par[kOffHeadB];
+                *reinterpret_cast<float4*>(a.raw + grow[t] * 4) =
+                    make_float4(c0 + s_par[kOffRgbB], c1 + s_par[kOffRgbB + 1], c2 + s_par[kOffRgbB + 2], sigma);
+              }
+            }
+          }
+          // ---- operands the NEXT layer needs besides the activations
+          if (l == 4) { enc_wait(); write_enc_x(grow[t]); }
+          if (l == 8) { enc_wait(); write_enc_d(grow[t]); }
+          if (l + 1 < sc.nlayers) signal_ready(t);
+          else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------- packing
+struct PackChunk {
+  const float* w;      // weight matrix [rows, ld]
+  int ld, col0, ncols; // source columns col0 .. col0+ncols (rest of the 64 are zero)
+  int nrows;           // 256 or 128 (two CTA halves of nrows/2)
+  uint32_t off;        // blob offset
+};
+struct PackArgs {
+  PackChunk ch[kNumFullChunks + kNumViewChunks];
+  int nchunks;
+  const float* src[8];  // fp32 block sources, see pack kernel
+  int out_ch, use_viewdirs;
+  const float* bias[10];
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, uint8_t* __restrict__ blob, int chunk_area) {
+  const int c = blockIdx.y;
+  if (c < pa.nchunks) {
+    const PackChunk pc = pa.ch[c];
+    const int half_rows = pc.nrows / 2;
+    // one thread per 16-byte unit: nrows x 8 units
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < pc.nrows * 8; idx += gridDim.x * blockDim.x) {
+      const int n = idx >> 3, u = idx & 7;
+      const int half = n / half_rows, r = n % half_rows;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = 8 * u + j;
+        f[j] = (k < pc.ncols) ? __ldg(pc.w + (size_t)n * pc.ld + pc.col0 + k) : 0.f;
+      }
+      uint4 v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                           pack_bf16x2(f[6], f[7]));
+      *reinterpret_cast<uint4*>(blob + pc.off + (size_t)half * half_rows * 128 + sw128_offset(r, u)) = v;
+    }
+  } else if (blockIdx.x == 0) {
+    // fp32 parameter block
+    float* par = reinterpret_cast<float*>(blob + chunk_area);
+    for (int i = threadIdx.x; i < kParamFloats; i += blockDim.x) {
+      float v = 0.f;
+      if (i < kOffBiasFeat) {
+        v = pa.bias[i >> 8][i & 255];
+      } else if (i < kOffBiasViews) {
+        if (pa.use_viewdirs) v = pa.bias[8][i - kOffBiasFeat];
+      } else if (i < kOffHeadW) {
+        if (pa.use_viewdirs) v = pa.bias[9][i - kOffBiasViews];
+      } else if (i < kOffRgbW) {
+        const int j = i - kOffHeadW;              // head weights [k][256]
+        const int rows = pa.use_viewdirs ? 1 : pa.out_ch;
+        if (j < rows * 256) v = pa.src[0][j];
+      } else if (i < kOffHeadB) {
+        if (pa.use_viewdirs) v = pa.src[2][i - kOffRgbW];   // rgb_linear.weight [3,128]
+      } else if (i < kOffRgbB) {
+        const int j = i - kOffHeadB;
+        const int rows = pa.use_viewdirs ? 1 : pa.out_ch;
+        if (j < rows) v = pa.src[1][j];
+      } else {
+        const int j = i - kOffRgbB;
+        if (pa.use_viewdirs && j < 3) v = pa.src[3][j];
+      }
+      par[i] = v;
+    }
+  }
+}
+
+}  // namespace nerfb
+
+using namespace nerfb;
+
+extern "C" size_t nerfb_packed_weights_bytes(int use_viewdirs) {
+  return (size_t)(use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD) + kParamBytes;
+}
+
+extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs, int out_ch, void* packed,
+                                  void* stream) {
+  NERFB_REQUIRE(h_params && packed, "nerfb_pack_weights: null argument");
+  for (int i = 0; i < 16; ++i) NERFB_REQUIRE(h_params[i], "nerfb_pack_weights: pts_linears parameter %d missing", i);
+  PackArgs pa{};
+  pa.use_viewdirs = use_viewdirs;
+  pa.out_ch = out_ch;
+  int n = 0;
+  auto add = [&](const float* w, int ld, int col0, int ncols, int nrows) {
+    const uint32_t off = n < kNumFullChunks ? (uint32_t)n * kChunkFull
+                                            : (uint32_t)kNumFullChunks * kChunkFull + (uint32_t)(n - kNumFullChunks) * kChunkViews;
+    pa.ch[n++] = PackChunk{w, ld, col0, ncols, nrows, off};
+  };
+  auto W = [&](int layer) { return h_params[2 * layer]; };
+  add(W(0), 63, 0, 63, 256);                                         // chunk 0
+  for (int l = 1; l <= 4; ++l)
+    for (int k = 0; k < 4; ++k) add(W(l), 256, 64 * k, 64, 256);     // 1..16
+  add(W(5), 319, 0, 63, 256);                                        // 17: gamma(x) part of the skip layer
+  for (int k = 0; k < 4; ++k) add(W(5), 319, 63 + 64 * k, 64, 256);  // 18..21
+  for (int l = 6; l <= 7; ++l)
+    for (int k = 0; k < 4; ++k) add(W(l), 256, 64 * k, 64, 256);     // 22..29
+  for (int l = 0; l < 8; ++l) pa.bias[l] = h_params[2 * l + 1];
+  if (use_viewdirs) {
+    const float* vw = h_params[NERFB_P_VIEWS_W];
+    const float* fw = h_params[NERFB_P_FEATURE_W];
+    NERFB_REQUIRE(vw && fw && h_params[NERFB_P_VIEWS_B] && h_params[NERFB_P_FEATURE_B] && h_params[NERFB_P_ALPHA_W] &&
+                      h_params[NERFB_P_ALPHA_B] && h_params[NERFB_P_RGB_W] && h_params[NERFB_P_RGB_B],
+                  "nerfb_pack_weights: view-dependent head parameters missing");
+    for (int k = 0; k < 4; ++k) add(fw, 256, 64 * k, 64, 256);       // 30..33 feature_linear
+    add(vw, 283, 256, 27, 128);                                      // 34: gamma(d) part [feature | gamma(d)]
+    for (int k = 0; k < 4; ++k) add(vw, 283, 64 * k, 64, 128);       // 35..38
+    pa.bias[8] = h_params[NERFB_P_FEATURE_B];
+    pa.bias[9] = h_params[NERFB_P_VIEWS_B];
+    pa.src[0] = h_params[NERFB_P_ALPHA_W];
+    pa.src[1] = h_params[NERFB_P_ALPHA_B];
+    pa.src[2] = h_params[NERFB_P_RGB_W];
+    pa.src[3] = h_params[NERFB_P_RGB_B];
+  } else {
+    NERFB_REQUIRE(out_ch >= 1 && out_ch <= 5 && h_params[NERFB_P_OUTPUT_W] && h_params[NERFB_P_OUTPUT_B],
+                  "nerfb_pack_weights: output_linear missing or out_ch=%d unsupported", out_ch);
+    pa.src[0] = h_params[NERFB_P_OUTPUT_W];
+    pa.src[1] = h_params[NERFB_P_OUTPUT_B];
+  }
+  pa.nchunks = n;
+  dim3 grid(2, n + 1);
+  pack_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(pa, (uint8_t*)packed,
+                                                          use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD);
+  return check_launch("pack_weights_kernel");
+}
+
+extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const float* z, const float* pts,
+                                  const float* viewdirs, int use_viewdirs, int out_ch, const void* packed, float* raw,
+                                  void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw, "nerfb_mlp_fwd_bf16: bad arguments");
+  NERFB_REQUIRE(use_viewdirs || (out_ch >= 1 && out_ch <= 5), "nerfb_mlp_fwd_bf16: out_ch=%d unsupported", out_ch);
+  NERFB_REQUIRE(pts || (rays && z && ray_width >= 8), "nerfb_mlp_fwd_bf16: need pts or rays+z");
+  NERFB_REQUIRE(!use_viewdirs || viewdirs || (rays && ray_width >= 11),
+                "nerfb_mlp_fwd_bf16: view directions requested but not provided");
+  if (R == 0) return NERFB_OK;
+  static Sched sched_vd, sched_novd;
+  static bool sched_init = false;
+  if (!sched_init) {
+    build_schedule(true, sched_vd);
+    build_schedule(false, sched_novd);
+    sched_init = true;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  MlpArgs a{};
+  a.rays = rays; a.rw = ray_width; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
+  a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = use_viewdirs;
+  a.packed = (const uint8_t*)packed; a.raw = raw;
+  a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
+  a.nclusters = sm_count() / 2;
+  if (a.nclusters > a.nst) a.nclusters = a.nst;
+  a.watch = get_watch();
+  a.out_ch = use_viewdirs ? 4 : out_ch;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * a.nclusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = as_stream(stream);
+  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_kernel, a, use_viewdirs ? sched_vd : sched_novd));
+  return check_launch("nerf_mlp_fwd_kernel");
 }

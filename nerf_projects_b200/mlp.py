@@ -211,7 +211,7 @@ def forward_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
     dev = net.pts_linears[0].weight.device
     ch = 4 if net.use_viewdirs else net.output_ch
     raw = torch.empty((R * S, ch), dtype=torch.float32, device=dev)
-    ops.mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, net.use_viewdirs, packed_weights(net), raw)
+    ops.mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, net.use_viewdirs, net.output_ch, packed_weights(net), raw)
     return raw
 
 

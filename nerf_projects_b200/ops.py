@@ -221,9 +221,9 @@ def pack_weights(param_ptrs: Sequence[Optional[int]], use_viewdirs: bool, out_ch
     _count()
 
 
-def mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, packed, raw):
+def mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, raw):
     L.check(L.load().nerfb_mlp_fwd_bf16(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
-                                        L.ptr(z), L.ptr(pts), L.ptr(viewdirs), int(bool(use_viewdirs)),
+                                        L.ptr(z), L.ptr(pts), L.ptr(viewdirs), int(bool(use_viewdirs)), int(out_ch),
                                         L.ptr(packed), L.ptr(raw), L.stream()), "nerfb_mlp_fwd_bf16")
     _count()
     return raw
