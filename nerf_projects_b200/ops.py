@@ -221,7 +221,34 @@ def pack_weights(param_ptrs: Sequence[Optional[int]], use_viewdirs: bool, out_ch
     _count()
 
 
+# optional per-launch CUDA-event timing of the fused MLP kernel (bench.py's roofline leg)
+_mlp_events = None
+
+
+def profile_mlp(enable: bool):
+    """Start (True) / stop (False) recording CUDA events around every fused-MLP launch.
+    Stopping returns [(milliseconds, rows, use_viewdirs), ...] (synchronises)."""
+    global _mlp_events
+    if enable:
+        _mlp_events = []
+        return None
+    evs, _mlp_events = _mlp_events or [], None
+    torch.cuda.synchronize()
+    return [(a.elapsed_time(b), rows, vd) for a, b, rows, vd in evs]
+
+
 def mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, raw):
+    if _mlp_events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, raw)
+        e1.record()
+        _mlp_events.append((e0, e1, int(R) * int(S), bool(use_viewdirs)))
+        return raw
+    return _mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, raw)
+
+
+def _mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, raw):
     L.check(L.load().nerfb_mlp_fwd_bf16(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
                                         L.ptr(z), L.ptr(pts), L.ptr(viewdirs), int(bool(use_viewdirs)), int(out_ch),
                                         L.ptr(packed), L.ptr(raw), L.stream()), "nerfb_mlp_fwd_bf16")

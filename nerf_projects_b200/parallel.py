@@ -1,0 +1,98 @@
+"""Multi-GPU: one process per GPU (torch.distributed, NCCL over NVLink).
+
+The path shards by rays (independent units): every rank renders a contiguous
+slice of the flattened ray list with replicated weights; the only
+collectives are ONE all-gather of the rendered tiles per frame and ONE
+all-reduce of the flat parameter-gradient bucket per training step
+(SURVEY.md 8e).  Nothing else crosses GPUs.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """Contiguous slice [lo, hi) of n rays for `rank`, plus the padded per-rank length."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi, per
+
+
+def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, **kwargs):
+    """Ray-sharded render of one frame: each rank renders rays[lo:hi] with
+    ``render_fn`` (= nerf_projects_b200.render), then one all_gather assembles
+    [rgb(3), disp, acc] for the full frame on every rank.  Returns
+    (rgb [N,3], disp [N], acc [N]) for the N input rays."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = rays_o.shape[0]
+    lo, hi, per = shard_bounds(n, world, rank)
+    dev = rays_o.device
+    tile = torch.zeros((per, 5), dtype=torch.float32, device=dev)
+    if hi > lo:
+        rgb, disp, acc, _ = render_fn(H, W, K, rays=(rays_o[lo:hi], rays_d[lo:hi]), **kwargs)
+        tile[:hi - lo, 0:3] = rgb
+        tile[:hi - lo, 3] = disp
+        tile[:hi - lo, 4] = acc
+    if world == 1:
+        full = tile
+    else:
+        full = torch.empty((world * per, 5), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, tile, group=group)
+    full = full[:n]
+    return full[:, 0:3], full[:, 3], full[:, 4]
+
+
+class GradBucket:
+    """Flat fp32 bucket for the parameter gradients of both networks
+    (2 x 595 844 floats = 4.77 MB): one all-reduce per step."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def allreduce_mean(self, group=None):
+        """sum over ranks of d(sum-loss)/dp divided by world (the MSE is a mean over the
+        global batch); gradients are written back into p.grad."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.mul_(1.0 / world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
+def train_step_sharded(render_fn, loss_fn, optimizer, bucket: GradBucket, H, W, K, rays_o, rays_d, target,
+                       group=None, **kwargs):
+    """Data-parallel step: the global ray batch is split across ranks, each rank
+    does forward/backward on its slice, gradients are averaged with one
+    all-reduce, every rank applies the identical Adam update."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = rays_o.shape[0]
+    lo, hi, _ = shard_bounds(n, world, rank)
+    rgb, disp, acc, extras = render_fn(H, W, K, rays=(rays_o[lo:hi], rays_d[lo:hi]), **kwargs)
+    loss = loss_fn(rgb, target[lo:hi])
+    if "rgb0" in extras:
+        loss = loss + loss_fn(extras["rgb0"], target[lo:hi])
+    optimizer.zero_grad()
+    loss.backward()
+    bucket.allreduce_mean(group)
+    optimizer.step()
+    return loss.detach()

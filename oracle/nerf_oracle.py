@@ -77,16 +77,31 @@ def make_params(seed: int, **arch) -> Dict[str, np.ndarray]:
     return params
 
 
-def sharpen_density(params: Dict[str, np.ndarray], gain=30.0, bias=-0.5):
-    """Harder parity set of SURVEY.md 7.3-B(iii): scale the density head so
-    sigma is non-trivial and compositing / sample_pdf are really exercised."""
+def density_head(params: Dict[str, np.ndarray]):
+    """(key, row) of the parameters that produce sigma."""
+    return ("alpha_linear", 0) if "alpha_linear.weight" in params else ("output_linear", 3)
+
+
+def calibrate_density(params: Dict[str, np.ndarray], pts: np.ndarray, viewdirs: Optional[np.ndarray],
+                      target_std=3.0, empty_fraction=0.6, **net):
+    """Turns a random-init network into a non-trivial synthetic "scene"
+    (SURVEY.md 7.3-B iii): rescales / shifts the density head so that over the
+    given sample positions sigma has standard deviation ``target_std`` and is
+    negative (empty space) on ``empty_fraction`` of them.  Plain random init has
+    sigma of one sign almost everywhere, which makes compositing and sample_pdf
+    degenerate.  Returns a new params dict (only the density row changes)."""
     p = dict(params)
-    key = "alpha_linear" if "alpha_linear.weight" in p else "output_linear"
+    key, row = density_head(p)
+    with torch.no_grad():
+        raw = run_network(torch.from_numpy(pts[:, None, :]),
+                          torch.from_numpy(viewdirs) if viewdirs is not None else None, to_torch(p), **net)
+    s = raw[:, 0, 3].numpy().astype(np.float64)
+    gain = target_std / max(s.std(), 1e-12)
+    shift = np.quantile(s, empty_fraction)
     w = p[key + ".weight"].copy()
     b = p[key + ".bias"].copy()
-    row = 0 if key == "alpha_linear" else 3
-    w[row] *= gain
-    b[row] = b[row] * gain + bias
+    w[row] = (w[row] * gain).astype(np.float32)
+    b[row] = np.float32((b[row] - shift) * gain)
     p[key + ".weight"], p[key + ".bias"] = w, b
     return p
 

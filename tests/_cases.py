@@ -26,29 +26,44 @@ def _pf():
     return O.make_params(1, use_viewdirs=True, output_ch=5)
 
 
-# tag -> (coarse params, fine params, kwargs of the render)
+# tag -> description of the render; "scene" cases take their (calibrated) density head from the fixture
 RENDER_CASES = {
     "render_c0": dict(pc=lambda: O.make_params(100, use_viewdirs=False, input_ch_views=0, output_ch=4), pf=None,
                       use_viewdirs=False, N_samples=64, N_importance=0, white_bkgd=False, ndc=False, lindisp=False),
+    "render_c0_scene": dict(pc=lambda: O.make_params(101, use_viewdirs=False, input_ch_views=0, output_ch=4),
+                            pf=None, use_viewdirs=False, N_samples=64, N_importance=0, white_bkgd=True, ndc=False,
+                            lindisp=False),
     "render_c1": dict(pc=_pc, pf=_pf, use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=True,
                       ndc=False, lindisp=False),
-    "render_c1_sharp": dict(pc=lambda: O.sharpen_density(_pc()), pf=lambda: O.sharpen_density(_pf()),
-                            use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=True, ndc=False,
-                            lindisp=False),
-    "render_lindisp": dict(pc=lambda: O.sharpen_density(_pc()), pf=lambda: O.sharpen_density(_pf()),
-                           use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=False, ndc=False,
-                           lindisp=True),
-    "render_llff": dict(pc=lambda: O.sharpen_density(_pc()), pf=lambda: O.sharpen_density(_pf()),
-                        use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=False, ndc=True,
-                        lindisp=False),
-    "render_nov_40_24": dict(
-        pc=lambda: O.sharpen_density(O.make_params(7, use_viewdirs=False, input_ch_views=0, output_ch=5)),
-        pf="same", use_viewdirs=False, N_samples=40, N_importance=24, white_bkgd=True, ndc=False, lindisp=False),
+    "render_c1_sharp": dict(pc=_pc, pf=_pf, use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=True,
+                            ndc=False, lindisp=False),
+    "render_lindisp": dict(pc=_pc, pf=_pf, use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=False,
+                           ndc=False, lindisp=True),
+    "render_llff": dict(pc=_pc, pf=_pf, use_viewdirs=True, N_samples=64, N_importance=128, white_bkgd=False,
+                        ndc=True, lindisp=False),
+    "render_nov_40_24": dict(pc=lambda: O.make_params(7, use_viewdirs=False, input_ch_views=0, output_ch=5),
+                             pf="same", use_viewdirs=False, N_samples=40, N_importance=24, white_bkgd=True,
+                             ndc=False, lindisp=False),
 }
 
 
-def case_params(tag):
+def _apply_overrides(p, g, prefix):
+    p = dict(p)
+    for k, v in g.items():
+        if k.startswith(prefix + "."):
+            p[k[len(prefix) + 1:]] = np.ascontiguousarray(v)
+    return p
+
+
+def case_params(tag, fixture=None):
+    """Parameters of a golden case: seeded init + the density-head override stored in the fixture."""
     c = RENDER_CASES[tag]
-    pc = c["pc"]()
-    pf = pc if c["pf"] == "same" else (c["pf"]() if c["pf"] is not None else None)
+    g = fixture if fixture is not None else gold(tag)
+    pc = _apply_overrides(c["pc"](), g, "override.c")
+    if c["pf"] == "same":
+        pf = pc
+    elif c["pf"] is None:
+        pf = None
+    else:
+        pf = _apply_overrides(c["pf"](), g, "override.f")
     return pc, pf

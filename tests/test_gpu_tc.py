@@ -70,7 +70,7 @@ def test_fused_bf16_mlp_vs_oracle(use_viewdirs, out_ch, R, S):
     # explicit-points entry (run_network drop-in) gives the same numbers
     raw2 = mlp.forward_bf16(net, R, S, None, None, pts=pts.reshape(-1, 3).to(DEV),
                             viewdirs=rays[:, 8:11].contiguous().to(DEV) if use_viewdirs else None).view(R, S, -1)
-    assert torch.equal(raw, raw2)
+    assert (raw - raw2).abs().max().item() < 1e-6
 
 
 def test_fused_bf16_mlp_many_tiles_consistent():
@@ -91,4 +91,9 @@ def test_fused_bf16_mlp_many_tiles_consistent():
     assert torch.isfinite(raw).all()
     for r0 in (0, 777, 4000):
         sub = mlp.forward_bf16(net, 50, S, rays[r0:r0 + 50].contiguous(), z[r0:r0 + 50].contiguous()).view(50, S, 4)
-        assert torch.equal(sub, raw[r0:r0 + 50]), r0
+        # not bitwise: the two row tiles of a CTA accumulate the K chunks of the skip / view layers in
+        # different orders (ring schedule), so a row's result depends on its tile slot at fp32-rounding level
+        d = (sub - raw[r0:r0 + 50]).abs().max().item()
+        assert d < 1e-3, (r0, d)
+    again = mlp.forward_bf16(net, R, S, rays, z).view(R, S, 4)
+    assert torch.equal(again, raw), "run-to-run nondeterminism (race)"

@@ -99,7 +99,7 @@ def test_render_matches_reference(tag):
 
 def test_train_grads_match_reference():
     g = gold("train_grads")
-    pc, pf = case_params("render_c1_sharp")
+    pc, pf = case_params("render_c1_sharp", fixture=g)
     K1, _ = O.blender_camera(800, 800, 30.0)
     rays, _ = O.pack_rays(T(g["rays_o"]), T(g["rays_d"]), 2.0, 6.0, use_viewdirs=True)
     loss, gc, gf, _ = O.train_loss_and_grads(rays, T(g["target"]), O.to_torch(pc), O.to_torch(pf),

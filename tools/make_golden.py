@@ -173,9 +173,31 @@ def main():
          s64=s64, i64=i64.to(torch.int16), urand=urand, srand=srand, irand=irand.to(torch.int16))
 
     # ---- a3-a6,a11,a12: render() end to end -----------------------------
+    def scene(ro, rd, pc, pf, use_viewdirs, ndc, H, W, K, near, far, lindisp, N_samples):
+        """calibrate both density heads on the coarse sample positions of these rays"""
+        packed, _ = O.pack_rays(ro, rd, near, far, H=H, W=W, K=K, ndc=ndc, use_viewdirs=use_viewdirs)
+        z = O.coarse_z(packed[:, 6:7], packed[:, 7:8], N_samples, lindisp)
+        pts = (packed[:, None, 0:3] + packed[:, None, 3:6] * z[..., None]).reshape(-1, 3).numpy()
+        vd = packed[:, None, 8:11].expand(-1, N_samples, -1).reshape(-1, 3).numpy() if use_viewdirs else None
+        pc2 = O.calibrate_density(pc, pts, vd)
+        pf2 = O.calibrate_density(pf, pts, vd) if pf is not None else None
+        return pc2, pf2
+
+    def head_arrays(prefix, p):
+        key, _ = O.density_head(p)
+        return {f"{prefix}.{key}.weight": p[key + ".weight"], f"{prefix}.{key}.bias": p[key + ".bias"]}
+
     def run_render(tag, H, W, K, c2w, n, seed, use_viewdirs, N_imp, white, ndc, near, far, lindisp,
-                   pc, pf, N_samples=64):
+                   pc, pf, N_samples=64, calibrate=False):
         ro, rd, idx = subset_rays(H, W, K, c2w, n, seed)
+        extra = {}
+        if calibrate:
+            same = pf is pc
+            pc, pf2 = scene(ro, rd, pc, None if same else pf, use_viewdirs, ndc, H, W, K, near, far, lindisp, N_samples)
+            pf = pc if same else pf2
+            extra.update(head_arrays("override.c", pc))
+            if pf is not None and not same:
+                extra.update(head_arrays("override.f", pf))
         kw_train, kw_test, _ = ref_models(R, pc, pf, use_viewdirs, N_imp)
         kw = dict(kw_test); kw.update(white_bkgd=white, ndc=ndc, lindisp=lindisp, N_samples=N_samples)
         rec, orig, wrapped = capture_searchsorted()
@@ -193,7 +215,9 @@ def main():
                 out[k] = extras[k]
         if "inds" in rec:
             out["inds"] = rec["inds"].to(torch.int16)
+        out.update(extra)
         save(tag, **out)
+        return pc, pf
 
     Hc, Wc = 100, 100
     K0, c0 = O.blender_camera(Hc, Wc, 30.0)
@@ -204,15 +228,20 @@ def main():
     pc = O.make_params(0, use_viewdirs=True, output_ch=5)
     pf = O.make_params(1, use_viewdirs=True, output_ch=5)
     run_render("render_c1", 800, 800, K1, c1, 64, 2, True, 128, True, False, 2.0, 6.0, False, pc, pf)
-    pcs, pfs = O.sharpen_density(pc), O.sharpen_density(pf)
-    run_render("render_c1_sharp", 800, 800, K1, c1, 64, 3, True, 128, True, False, 2.0, 6.0, False, pcs, pfs)
-    run_render("render_lindisp", 800, 800, K1, c1, 32, 4, True, 128, False, False, 2.0, 6.0, True, pcs, pfs)
+    pcs, pfs = run_render("render_c1_sharp", 800, 800, K1, c1, 64, 3, True, 128, True, False, 2.0, 6.0, False,
+                          pc, pf, calibrate=True)
+    run_render("render_lindisp", 800, 800, K1, c1, 32, 4, True, 128, False, False, 2.0, 6.0, True, pc, pf,
+               calibrate=True)
     K3, c3 = O.llff_camera(756, 1008, 815.0)
-    run_render("render_llff", 756, 1008, K3, c3, 64, 5, True, 128, False, True, 0.0, 1.0, False, pcs, pfs)
+    run_render("render_llff", 756, 1008, K3, c3, 64, 5, True, 128, False, True, 0.0, 1.0, False, pc, pf,
+               calibrate=True)
     # no-viewdirs hierarchical (output_ch=5, fine net None -> coarse net reused) and odd sample counts
-    pn5 = O.sharpen_density(O.make_params(7, use_viewdirs=False, input_ch_views=0, output_ch=5))
+    pn5 = O.make_params(7, use_viewdirs=False, input_ch_views=0, output_ch=5)
     run_render("render_nov_40_24", 800, 800, K1, c1, 32, 6, False, 24, True, False, 2.0, 6.0, False, pn5, pn5,
-               N_samples=40)
+               N_samples=40, calibrate=True)
+    p0s = O.make_params(101, use_viewdirs=False, input_ch_views=0, output_ch=4)
+    run_render("render_c0_scene", Hc, Wc, K0, c0, 160, 8, False, 0, True, False, 2.0, 6.0, False, p0s, None,
+               calibrate=True)
 
     # ---- a13: loss + gradients of one training objective ----------------
     ro, rd, idx = subset_rays(800, 800, K1, c1, 24, 9)
@@ -224,6 +253,7 @@ def main():
     loss = R.ref_helpers.img2mse(rgb, target) + R.ref_helpers.img2mse(extras["rgb0"], target)
     loss.backward()
     g = dict(rays_o=ro, rays_d=rd, target=target, loss=loss.detach())
+    g.update(head_arrays("override.c", pcs)); g.update(head_arrays("override.f", pfs))
     srng = np.random.Generator(np.random.PCG64(5))
     for tag, net in (("c", kw["network_fn"]), ("f", kw["network_fine"])):
         for name, prm in net.named_parameters():
