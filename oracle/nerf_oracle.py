@@ -77,6 +77,25 @@ def make_params(seed: int, **arch) -> Dict[str, np.ndarray]:
     return params
 
 
+def smooth_spectrum(params: Dict[str, np.ndarray], falloff=0.5, input_ch=63, skips=(4,)):
+    """Damps the weights that read frequency band k of gamma(x) by falloff**k (first layer and
+    the gamma(x) columns of the skip layers).  A random-init network is white noise at the
+    2^9 band -- sigma changes by O(1) between adjacent samples, unlike any trained field -- which
+    turns the (legitimately discontinuous) resampling step into a chaos amplifier.  The damped
+    network is a band-limited synthetic scene.  Deterministic; only those columns change."""
+    p = dict(params)
+    L = (input_ch - 3) // 6
+    scale = np.ones(input_ch, np.float32)
+    for k in range(L):
+        scale[3 + 6 * k: 3 + 6 * k + 6] = np.float32(falloff ** k)
+    names = ["pts_linears.0.weight"] + [f"pts_linears.{i + 1}.weight" for i in skips]
+    for n in names:
+        w = p[n].copy()
+        w[:, :input_ch] *= scale
+        p[n] = w
+    return p
+
+
 def density_head(params: Dict[str, np.ndarray]):
     """(key, row) of the parameters that produce sigma."""
     return ("alpha_linear", 0) if "alpha_linear.weight" in params else ("output_linear", 3)

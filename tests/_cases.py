@@ -56,14 +56,29 @@ def _apply_overrides(p, g, prefix):
 
 
 def case_params(tag, fixture=None):
-    """Parameters of a golden case: seeded init + the density-head override stored in the fixture."""
+    """Parameters of a golden case: seeded init; "scene" cases additionally get the band-limiting of
+    O.smooth_spectrum and the calibrated density head stored in the fixture."""
     c = RENDER_CASES[tag]
     g = fixture if fixture is not None else gold(tag)
-    pc = _apply_overrides(c["pc"](), g, "override.c")
+    scene = any(k.startswith("override.") for k in g)
+    sm = O.smooth_spectrum if scene else (lambda p: p)
+    pc = _apply_overrides(sm(c["pc"]()), g, "override.c")
     if c["pf"] == "same":
         pf = pc
     elif c["pf"] is None:
         pf = None
     else:
-        pf = _apply_overrides(c["pf"](), g, "override.f")
+        pf = _apply_overrides(sm(c["pf"]()), g, "override.f")
     return pc, pf
+
+
+def maps_close(got, ref, tol, min_frac=1.0, cap=None, what=""):
+    """|got-ref| <= tol on at least ``min_frac`` of the rays and <= cap on all of
+    them.  Returns the number of rays outside ``tol`` (the reported outlier set)."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref).reshape(got.shape[0], -1).max(-1)
+    bad = err > tol
+    assert (~bad).mean() >= min_frac, f"{what}: only {(~bad).mean():.3f} of rays within {tol} (max err {err.max():.3e})"
+    if cap is not None:
+        assert err.max() <= cap, f"{what}: max err {err.max():.3e} > cap {cap}"
+    return int(bad.sum())

@@ -173,14 +173,14 @@ def main():
          s64=s64, i64=i64.to(torch.int16), urand=urand, srand=srand, irand=irand.to(torch.int16))
 
     # ---- a3-a6,a11,a12: render() end to end -----------------------------
-    def scene(ro, rd, pc, pf, use_viewdirs, ndc, H, W, K, near, far, lindisp, N_samples):
+    def scene(ro, rd, pc, pf, use_viewdirs, ndc, H, W, K, near, far, lindisp, N_samples, target_std=3.0):
         """calibrate both density heads on the coarse sample positions of these rays"""
         packed, _ = O.pack_rays(ro, rd, near, far, H=H, W=W, K=K, ndc=ndc, use_viewdirs=use_viewdirs)
         z = O.coarse_z(packed[:, 6:7], packed[:, 7:8], N_samples, lindisp)
         pts = (packed[:, None, 0:3] + packed[:, None, 3:6] * z[..., None]).reshape(-1, 3).numpy()
         vd = packed[:, None, 8:11].expand(-1, N_samples, -1).reshape(-1, 3).numpy() if use_viewdirs else None
-        pc2 = O.calibrate_density(pc, pts, vd)
-        pf2 = O.calibrate_density(pf, pts, vd) if pf is not None else None
+        pc2 = O.calibrate_density(pc, pts, vd, target_std=target_std)
+        pf2 = O.calibrate_density(pf, pts, vd, target_std=target_std) if pf is not None else None
         return pc2, pf2
 
     def head_arrays(prefix, p):
@@ -188,12 +188,15 @@ def main():
         return {f"{prefix}.{key}.weight": p[key + ".weight"], f"{prefix}.{key}.bias": p[key + ".bias"]}
 
     def run_render(tag, H, W, K, c2w, n, seed, use_viewdirs, N_imp, white, ndc, near, far, lindisp,
-                   pc, pf, N_samples=64, calibrate=False):
+                   pc, pf, N_samples=64, calibrate=False, target_std=3.0):
         ro, rd, idx = subset_rays(H, W, K, c2w, n, seed)
         extra = {}
         if calibrate:
             same = pf is pc
-            pc, pf2 = scene(ro, rd, pc, None if same else pf, use_viewdirs, ndc, H, W, K, near, far, lindisp, N_samples)
+            pc = O.smooth_spectrum(pc)
+            pf = pc if same else (O.smooth_spectrum(pf) if pf is not None else None)
+            pc, pf2 = scene(ro, rd, pc, None if same else pf, use_viewdirs, ndc, H, W, K, near, far, lindisp, N_samples,
+                            target_std)
             pf = pc if same else pf2
             extra.update(head_arrays("override.c", pc))
             if pf is not None and not same:
@@ -238,7 +241,7 @@ def main():
     # no-viewdirs hierarchical (output_ch=5, fine net None -> coarse net reused) and odd sample counts
     pn5 = O.make_params(7, use_viewdirs=False, input_ch_views=0, output_ch=5)
     run_render("render_nov_40_24", 800, 800, K1, c1, 32, 6, False, 24, True, False, 2.0, 6.0, False, pn5, pn5,
-               N_samples=40, calibrate=True)
+               N_samples=40, calibrate=True, target_std=1.5)   # 64 evals/ray only: gentler density
     p0s = O.make_params(101, use_viewdirs=False, input_ch_views=0, output_ch=4)
     run_render("render_c0_scene", Hc, Wc, K0, c0, 160, 8, False, 0, True, False, 2.0, 6.0, False, p0s, None,
                calibrate=True)
