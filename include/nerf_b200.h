@@ -181,6 +181,10 @@ int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const flo
  * of 32 (<= 256).  Used by tests only. */
 int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float* B, float* C,
                         void* stream);
+/* Debug: when dev_buf != NULL, block 0 of the fused MLP kernel records a clock64 timeline
+ * (3 regions x 4096 entries: loader, MMA issuer, epilogue; entry = tag<<44 | cycles).
+ * Pass NULL to switch tracing off. */
+int nerfb_set_trace(long long* dev_buf);
 /* Host pointer to the 8 x u64 watchdog record the tensor-core kernels write
  * before trapping when a barrier wait times out ([0]=0xDEAD when fired). */
 const unsigned long long* nerfb_watchdog_record(void);

@@ -65,16 +65,18 @@ constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
 constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
 constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
 constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
-constexpr int kNumBars = 3 * kNS + 2 + 2 + 1;           // w_full, w_peer, w_empty, act_ready[2], mma_done[2], enc_free
+constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
 constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
-constexpr int kSmemBytes = kSmTmemSlot + 16;
+constexpr int kSmOps = kSmTmemSlot + 16;                 // copy of Sched::ops (u32 each)
+constexpr int kSmemBytes = kSmOps + 84 * 4;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 
 // ------------------------------------------------------------- schedule
 // A static program shared by the three asynchronous roles.  Generated on the
 // host (build_schedule) and passed by value.
 struct LoadEnt { uint32_t off; uint32_t bytes; };          // blob offset of the chunk, bytes per CTA
-enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16 };
+enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16,
+               F_BLOCK4 = 32 };   // this op and the next 3: one tile's pass over 4 resident chunks, issued back to back
 struct OpEnt { uint8_t load, tile, asrc, flags; };          // asrc 0..3 = act chunk, 4 = enc
 struct Sched {
   int nloads, nops, nlayers;
@@ -102,7 +104,8 @@ static void build_schedule(bool vd, Sched& s) {
     for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
     const int f = n128 ? F_N128 : 0;
     for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
-    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
+    for (int k = 0; k < 4; ++k)
+      add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST | F_BLOCK4 : 0) | (k == 3 ? F_LAST : 0));
   };
   // layer with an extra K=64 chunk read from the enc buffer (skip concat / view concat):
   // tile A consumes it first, tile B last, so the 4-slot ring never needs 5 live chunks.
@@ -114,7 +117,7 @@ static void build_schedule(bool vd, Sched& s) {
     const uint8_t g2 = add_load(id_enc, n128);
     add_op(g, 0, 4, f | F_FIRST | F_REL_SLOT | F_REL_ENC);
     for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 3 ? F_LAST : 0));
-    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0));
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST | F_BLOCK4 : 0));
     add_op(g2, 1, 4, f | F_LAST | F_REL_SLOT | F_REL_ENC);
   };
   {  // layer 0: K = 64 (gamma(x)), one chunk used by both tiles
@@ -139,7 +142,10 @@ struct MlpArgs {
   const uint8_t* packed; float* raw;
   int nst, nclusters;
   Watch watch;
+  long long* trace;   // debug timeline (nerfb_set_trace), 3 regions of kTraceLen entries
 };
+constexpr int kTraceLen = 4096;
+static long long* g_trace = nullptr;
 
 // ------------------------------------------------------------- encoding
 // value of column c of gamma(p) (embedder.py:54-65): [p | sin f0 p | cos f0 p | sin f1 p | ...]
@@ -193,15 +199,20 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
   float* s_par = reinterpret_cast<float*>(smem + kSmParams);
   float* s_sig = reinterpret_cast<float*>(smem + kSmSig);
   auto bar = [&](int i) -> uint32_t { return sbase + kSmBars + 8 * i; };
-  const int B_FULL = 0, B_PEER = kNS, B_EMPTY = 2 * kNS, B_ACT = 3 * kNS, B_DONE = 3 * kNS + 2, B_ENC = 3 * kNS + 4;
+  const int B_FULL = 0, B_EMPTY = kNS, B_ACT = 2 * kNS, B_DONE = 2 * kNS + 2, B_ENC = 2 * kNS + 4;
 
   if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xA11, sbase, 0);
+  const bool tracing = (a.trace != nullptr) && blockIdx.x == 0;
+  int tr_n = 0;
+  auto tr = [&](int region, int tag) {
+    if (tracing && tr_n < kTraceLen) a.trace[region * kTraceLen + tr_n++] = ((long long)tag << 44) | (clock64() & 0xFFFFFFFFFFFll);
+  };
 
   // ---- one-time setup
   if (tid == 0) {
     for (int s = 0; s < kNS; ++s) {
-      mbar_init(bar(B_FULL + s), 1);
-      mbar_init(bar(B_PEER + s), 1);
+      // leader: own loader (arrive.expect_tx) + the peer's relay (remote arrive) -> ONE barrier per slot
+      mbar_init(bar(B_FULL + s), rank == 0 ? 2 : 1);
       mbar_init(bar(B_EMPTY + s), 1);
     }
     mbar_init(bar(B_ACT + 0), 2);
@@ -210,6 +221,11 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
     mbar_init(bar(B_DONE + 1), 1);
     mbar_init(bar(B_ENC), 1);
     fence_barrier_init();
+  }
+  for (int i = tid; i < sc.nops; i += kThreads) {
+    const OpEnt e = sc.ops[i];
+    reinterpret_cast<uint32_t*>(smem + kSmOps)[i] =
+        (uint32_t)e.load | ((uint32_t)e.tile << 8) | ((uint32_t)e.asrc << 16) | ((uint32_t)e.flags << 24);
   }
   {
     const float* gpar = reinterpret_cast<const float*>(a.packed + (a.use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD));
@@ -234,6 +250,7 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
         for (int q = 0; q < sc.nloads; ++q, ++gl) {
           const int slot = (int)(gl % kNS);
           if (gl >= kNS) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((gl / kNS) + 1) & 1), a.watch, 0x100 + q);
+          tr(0, 0x100 + q);
           const LoadEnt le = sc.loads[q];
           mbar_arrive_expect_tx(bar(B_FULL + slot), le.bytes);
           bulk_g2s(sbase + kSmRing + slot * kChunkBytes, a.packed + le.off + (size_t)rank * le.bytes, le.bytes,
@@ -249,42 +266,105 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
         for (int q = 0; q < sc.nloads; ++q, ++gl) {
           const int slot = (int)(gl % kNS);
           mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x200 + q);
-          mbar_arrive_cluster(bar(B_PEER + slot), 0);
+          mbar_arrive_remote(bar(B_FULL + slot), 0);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread)
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA)
+    // tcgen05.mma issue is back-pressured by execution (the queue is ~1 MMA deep, see the
+    // timeline in profiles/), so every cycle spent between two MMAs idles the tensor core:
+    //  * the WHOLE warp runs this loop with warp-uniform control flow and operands derived
+    //    only from uniform sources (kernel params, constants), so descriptors live in
+    //    uniform registers; a divergent `if (lane == 0)` made ptxas wrap every UTCHMMA in a
+    //    waterfall loop of 7 R2UR.BROADCAST (~170 cycles per MMA instead of 128);
+    //  * ONE weights barrier per slot, no wait at all for the second tile's pass over a
+    //    resident chunk, and the barrier probes of op o+1 are issued BEFORE the MMAs of op o.
+    if (rank == 0) {
+      // the whole TMEM (512 columns) is allocated, so its base address is 0: keep it a constant
+      if (tmem_base != 0) watchdog_fire(a.watch, 0xA12, tmem_base, 0);
       const uint32_t idesc256 = make_idesc_bf16(256, 256), idesc128 = make_idesc_bf16(256, 128);
-      uint32_t act_cnt[2] = {0, 0};
-      for (int it = 0; it < niter; ++it) {
-        const long long gl0 = (long long)it * sc.nloads;
-        for (int o = 0; o < sc.nops; ++o) {
-          const OpEnt op = sc.ops[o];
-          const long long gl = gl0 + op.load;
-          const int slot = (int)(gl % kNS);
-          const uint32_t par = (uint32_t)((gl / kNS) & 1);
-          if (op.flags & F_FIRST) {
-            mbar_wait(bar(B_ACT + op.tile), act_cnt[op.tile] & 1, a.watch, 0x300 + o);
-            act_cnt[op.tile]++;
-          }
-          mbar_wait(bar(B_FULL + slot), par, a.watch, 0x400 + o);
-          mbar_wait(bar(B_PEER + slot), par, a.watch, 0x500 + o);
-          tc_fence_after();
-          const uint32_t a_addr = (op.asrc < 4) ? (sbase + kSmAct + (op.tile * 4 + op.asrc) * kChunkBytes)
-                                                : (sbase + kSmEnc);
-          const uint64_t da = make_sdesc_sw128(a_addr);
-          const uint64_t db = make_sdesc_sw128(sbase + kSmRing + slot * kChunkBytes);
-          const uint32_t d_tmem = tmem_base + op.tile * 256;
-          const uint32_t idesc = (op.flags & F_N128) ? idesc128 : idesc256;
+      const uint64_t desc_hi = make_sdesc_sw128(0);            // everything but the start address
+      uint32_t act_cnt0 = 0, act_cnt1 = 0;
+      int confirmed = 0;                                       // loads [0, confirmed) are known to have landed
+      const int nops = sc.nops, nloads = sc.nloads;
+      const int total_ops = niter * nops;
+      auto fetch = [&](int o) -> uint32_t {
+        const OpEnt e = sc.ops[o];                             // uniform index -> ULDC from the param bank
+        return (uint32_t)e.load | ((uint32_t)e.tile << 8) | ((uint32_t)e.asrc << 16) | ((uint32_t)e.flags << 24);
+      };
+      uint32_t cur = fetch(0);
+      int gl = (int)(cur & 0xFF);
+      bool ok_act = false, ok_w = false;
+      int o = 0, gl0 = 0;
+      for (int n = 0; n < total_ops;) {
+        const int tile = (cur >> 8) & 0xFF, asrc = (cur >> 16) & 0xFF;
+        const uint32_t flags = cur >> 24;
+        const int slot = gl & (kNS - 1);
+        bool waited = false;
+        if (flags & F_FIRST) {
+          const uint32_t cnt = tile ? act_cnt1 : act_cnt0;
+          if (!ok_act) mbar_wait(bar(B_ACT + tile), cnt & 1, a.watch, 0x300 + o);
+          if (tile) ++act_cnt1; else ++act_cnt0;
+          waited = true;
+          if (lane == 0) tr(1, 0x300 + o);
+        }
+        if (gl >= confirmed) {
+          if (!ok_w) mbar_wait(bar(B_FULL + slot), (uint32_t)((gl >> 2) & 1), a.watch, 0x400 + o);
+          confirmed = gl + 1;
+          waited = true;
+        }
+        if (lane == 0) tr(1, 0x500 + o);
+        if (waited) tc_fence_after();
+        const uint32_t d_tmem = (uint32_t)tile * 256u;
+        const uint32_t idesc = (flags & F_N128) ? idesc128 : idesc256;
+        const uint32_t a_addr = (asrc < 4) ? (sbase + kSmAct + (tile * 4 + asrc) * kChunkBytes) : (sbase + kSmEnc);
+        const uint64_t da = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+        int adv;
+        if (flags & F_BLOCK4) {
+          // second tile's pass: the 4 chunks (loads gl..gl+3) are resident and already confirmed
+          const uint32_t last_flags = (uint32_t)sc.ops[o + 3].flags;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16<2>(d_tmem, sdesc_advance_k(da, k), sdesc_advance_k(db, k), idesc,
-                         ((op.flags & F_FIRST) && k == 0) ? 0u : 1u);
-          if (op.flags & F_REL_SLOT) umma_commit<2>(bar(B_EMPTY + slot));
-          if (op.flags & F_REL_ENC) umma_commit<2>(bar(B_ENC));
-          if (op.flags & F_LAST) umma_commit<2>(bar(B_DONE + op.tile));
+            for (int k = 0; k < 4; ++k) {
+              const int sl = (gl + k) & (kNS - 1);
+              const uint64_t dak = da + (uint64_t)(k * (kChunkBytes >> 4));
+              const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + sl * kChunkBytes) >> 4) & 0x3FFF);
+              umma_bf16<2>(d_tmem, dak, db, idesc, k == 0 ? 0u : 1u);
+              umma_bf16<2>(d_tmem, dak + 2, db + 2, idesc, 1u);
+              umma_bf16<2>(d_tmem, dak + 4, db + 4, idesc, 1u);
+              umma_bf16<2>(d_tmem, dak + 6, db + 6, idesc, 1u);
+              umma_commit<2>(bar(B_EMPTY + sl));
+            }
+            if (last_flags & F_LAST) umma_commit<2>(bar(B_DONE + tile));
+          }
+          adv = 4;
+        } else {
+          const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + slot * kChunkBytes) >> 4) & 0x3FFF);
+          if (elect_one()) {
+            umma_bf16<2>(d_tmem, da, db, idesc, (flags & F_FIRST) ? 0u : 1u);
+            umma_bf16<2>(d_tmem, da + 2, db + 2, idesc, 1u);
+            umma_bf16<2>(d_tmem, da + 4, db + 4, idesc, 1u);
+            umma_bf16<2>(d_tmem, da + 6, db + 6, idesc, 1u);
+            if (flags & F_REL_SLOT) umma_commit<2>(bar(B_EMPTY + slot));
+            if (flags & F_REL_ENC) umma_commit<2>(bar(B_ENC));
+            if (flags & F_LAST) umma_commit<2>(bar(B_DONE + tile));
+          }
+          adv = 1;
+        }
+        __syncwarp();
+        if (lane == 0) tr(1, 0x600 + o);
+        // ---- next op: table entry and (while the last MMA above is still executing) barrier probes
+        n += adv;
+        o += adv;
+        if (o >= nops) { o -= nops; gl0 += nloads; }
+        if (n < total_ops) {
+          cur = fetch(o);
+          gl = gl0 + (int)(cur & 0xFF);
+          const int tile2 = (cur >> 8) & 0xFF;
+          ok_act = ok_w = false;
+          if ((cur >> 24) & F_FIRST) ok_act = mbar_try_wait(bar(B_ACT + tile2), (tile2 ? act_cnt1 : act_cnt0) & 1);
+          if (gl >= confirmed) ok_w = mbar_try_wait(bar(B_FULL + (gl & (kNS - 1))), (uint32_t)((gl >> 2) & 1));
         }
       }
     }
@@ -306,7 +386,7 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
       tc_fence_before();
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et == 0) mbar_arrive_cluster(bar(B_ACT + t), 0);
+      if (et == 0) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
     };
     // sample position of my row in tile t
     auto load_point = [&](long long grow, float (&p)[3]) {
@@ -360,6 +440,7 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
         for (int t = 0; t < 2; ++t) {
           mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + l * 2 + t);
           done_cnt[t]++;
+          if (et == 0) tr(2, 0x700 + l * 2 + t);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + t * 256;
           if (l <= 8 && !(l == 7 && !vd)) {
@@ -368,35 +449,39 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
             const float* hw = s_par + kOffHeadW + 128 * hh;
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
             float sig = 0.f;
-#pragma unroll 1
+            // software pipeline: the TMEM load of batch b+1 is in flight while batch b is processed
+            uint32_t v[2][32];
+            tmem_ld32(taddr + 128 * hh, v[0]);
+#pragma unroll
             for (int b = 0; b < 4; ++b) {
-              uint32_t v[32];
-              tmem_ld32(taddr + 128 * hh + 32 * b, v);
               tmem_ld_wait();
+              if (b < 3) tmem_ld32(taddr + 128 * hh + 32 * (b + 1), v[(b + 1) & 1]);
+              const uint32_t (&vv)[32] = v[b & 1];
               float x[32];
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 bb = *reinterpret_cast<const float4*>(bias + 32 * b + 4 * j4);
-                x[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + bb.x;
-                x[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + bb.y;
-                x[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + bb.z;
-                x[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + bb.w;
-              }
-              if (l != 8) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                x[4 * j4 + 0] = __uint_as_float(vv[4 * j4 + 0]) + bb.x;
+                x[4 * j4 + 1] = __uint_as_float(vv[4 * j4 + 1]) + bb.y;
+                x[4 * j4 + 2] = __uint_as_float(vv[4 * j4 + 2]) + bb.z;
+                x[4 * j4 + 3] = __uint_as_float(vv[4 * j4 + 3]) + bb.w;
               }
               if (l == 7) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   const float4 ww = *reinterpret_cast<const float4*>(hw + 32 * b + 4 * j4);
-                  sig = fmaf(x[4 * j4 + 0], ww.x, sig); sig = fmaf(x[4 * j4 + 1], ww.y, sig);
-                  sig = fmaf(x[4 * j4 + 2], ww.z, sig); sig = fmaf(x[4 * j4 + 3], ww.w, sig);
+                  sig = fmaf(fmaxf(x[4 * j4 + 0], 0.f), ww.x, sig); sig = fmaf(fmaxf(x[4 * j4 + 1], 0.f), ww.y, sig);
+                  sig = fmaf(fmaxf(x[4 * j4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(x[4 * j4 + 3], 0.f), ww.w, sig);
                 }
               }
               uint32_t w[16];
+              if (l != 8) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+                for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2_relu(x[2 * i], x[2 * i + 1]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+              }
               const int col0 = 128 * hh + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
             }
@@ -456,6 +541,7 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
           // ---- operands the NEXT layer needs besides the activations
           if (l == 4) { enc_wait(); write_enc_x(grow[t]); }
           if (l == 8) { enc_wait(); write_enc_d(grow[t]); }
+          if (et == 0) tr(2, 0x800 + l * 2 + t);
           if (l + 1 < sc.nlayers) signal_ready(t);
           else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
         }
@@ -536,6 +622,11 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, uint8_t
 }  // namespace nerfb
 
 using namespace nerfb;
+
+extern "C" int nerfb_set_trace(long long* dev_buf) {
+  g_trace = dev_buf;
+  return NERFB_OK;
+}
 
 extern "C" size_t nerfb_packed_weights_bytes(int use_viewdirs) {
   return (size_t)(use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD) + kParamBytes;
@@ -620,6 +711,7 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
   a.nclusters = sm_count() / 2;
   if (a.nclusters > a.nst) a.nclusters = a.nst;
   a.watch = get_watch();
+  a.trace = g_trace;
   a.out_ch = use_viewdirs ? 4 : out_ch;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * a.nclusters);

@@ -30,6 +30,18 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 
+// one lane of a fully converged warp (the pattern tcgen05 issue wants: the surrounding
+// control flow stays warp-uniform so operands can live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- watchdog
 // Every wait is bounded: on timeout a record is written to host-mapped memory
 // (survives the trap) and the kernel traps, so a protocol bug is an error with
@@ -65,6 +77,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
   const uint32_t remote = mapa(bar, rank);
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// same with the default (CTA-scope release) semantics, as cutlass::arch::ClusterBarrier::arrive(cta_id):
+// used where the guarded data is consumed by the async/tensor proxy of the SM that wrote it
+// (after fence.proxy.async + a CTA barrier), so no cluster-scope memory fence is needed.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  const uint32_t remote = mapa(bar, rank);
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -93,10 +112,14 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 }
 constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s at 2 GHz
 
+// CTA-scope acquire (what CUTLASS's ClusterBarrier::wait uses, also for barriers with
+// remote arrivals): a cluster-scope acquire makes ptxas emit CCTL.IVALL (L1 invalidate)
+// after every wait, which was the top stall of the epilogue warps (profiles/r01).
+// The data guarded by these barriers is read through the async/tensor proxy or TMEM.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, Watch w, uint32_t tag) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
+  while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kWatchdogCycles) watchdog_fire(w, tag, bar, parity);
   }
 }
@@ -150,6 +173,54 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// One scheduled "op" of the fused MLP kernel as a single instruction sequence, executed by a
+// fully converged warp: (optional) non-blocking probes of the barriers the NEXT op needs, then
+// four K=16 MMAs (cta_group::2) and up to three commits issued by one elected lane, and only
+// then the probe results are read -- so the ~90-cycle try_wait latency overlaps the MMA issue
+// instead of idling the tensor core (whose queue is ~1 MMA deep).
+__device__ __forceinline__ void umma_op4_cg2(uint32_t d_tmem, uint64_t da0, uint64_t da1, uint64_t da2, uint64_t da3,
+                                             uint64_t db0, uint64_t db1, uint64_t db2, uint64_t db3, uint32_t idesc,
+                                             uint32_t acc0, uint32_t bar_rel, uint32_t f_rel, uint32_t bar_enc,
+                                             uint32_t f_enc, uint32_t bar_done, uint32_t f_done, uint32_t need_w,
+                                             uint32_t bar_w, uint32_t par_w, uint32_t need_a, uint32_t bar_a,
+                                             uint32_t par_a, uint32_t& ok_w, uint32_t& ok_a) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred Pe, Pacc, Pw, Pa, Pnw, Pna, Pf, Pc, Pt;\n\t"
+      ".reg .b16 mask;\n\t"
+      "mov.u16 mask, 3;\n\t"
+      "setp.eq.b32 Pt, 0, 0;\n\t"
+      "setp.ne.b32 Pnw, %19, 0;\n\t"
+      "setp.eq.b32 Pw, %19, 0;\n\t"
+      "setp.ne.b32 Pna, %22, 0;\n\t"
+      "setp.eq.b32 Pa, %22, 0;\n\t"
+      "@Pnw mbarrier.try_wait.parity.shared::cta.b64 Pw, [%20], %21;\n\t"
+      "@Pna mbarrier.try_wait.parity.shared::cta.b64 Pa, [%23], %24;\n\t"
+      "elect.sync _|Pe, 0xffffffff;\n\t"
+      "setp.ne.b32 Pacc, %12, 0;\n\t"
+      "@Pe tcgen05.mma.cta_group::2.kind::f16 [%2], %3, %7, %11, Pacc;\n\t"
+      "@Pe tcgen05.mma.cta_group::2.kind::f16 [%2], %4, %8, %11, Pt;\n\t"
+      "@Pe tcgen05.mma.cta_group::2.kind::f16 [%2], %5, %9, %11, Pt;\n\t"
+      "@Pe tcgen05.mma.cta_group::2.kind::f16 [%2], %6, %10, %11, Pt;\n\t"
+      "setp.ne.b32 Pf, %14, 0;\n\t"
+      "and.pred Pc, Pe, Pf;\n\t"
+      "@Pc tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%13], mask;\n\t"
+      "setp.ne.b32 Pf, %16, 0;\n\t"
+      "and.pred Pc, Pe, Pf;\n\t"
+      "@Pc tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%15], mask;\n\t"
+      "setp.ne.b32 Pf, %18, 0;\n\t"
+      "and.pred Pc, Pe, Pf;\n\t"
+      "@Pc tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%17], mask;\n\t"
+      "selp.u32 %0, 1, 0, Pw;\n\t"
+      "selp.u32 %1, 1, 0, Pa;\n\t"
+      "}"
+      : "=r"(ok_w), "=r"(ok_a)
+      : "r"(d_tmem), "l"(da0), "l"(da1), "l"(da2), "l"(da3), "l"(db0), "l"(db1), "l"(db2), "l"(db3), "r"(idesc),
+        "r"(acc0), "r"(bar_rel), "r"(f_rel), "r"(bar_enc), "r"(f_enc), "r"(bar_done), "r"(f_done), "r"(need_w),
+        "r"(bar_w), "r"(par_w), "r"(need_a), "r"(bar_a), "r"(par_a)
+      : "memory");
 }
 
 // all previously issued MMAs of this thread complete -> arrive(1) on `bar`
@@ -208,8 +279,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// max(x,0) fused into the conversion
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 }  // namespace tc05

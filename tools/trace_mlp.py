@@ -1,0 +1,43 @@
+"""Timeline of the fused MLP kernel (block 0): prints per-event cycle offsets (debug aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import nerf_projects_b200 as nb
+from nerf_projects_b200 import mlp, _lib
+from oracle import nerf_oracle as O
+
+net = nb.NeRF(8, 256, 63, 27, 5, [4], True).cuda()
+net.load_state_dict(O.to_torch(O.make_params(0, use_viewdirs=True, output_ch=5)))
+R, S = 32768, 192
+g = torch.Generator().manual_seed(0)
+rays = torch.cat([torch.randn(R, 3, generator=g), torch.randn(R, 3, generator=g), torch.full((R, 1), 2.), torch.full((R, 1), 6.),
+                  torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)], -1).cuda()
+z = (torch.rand(R, S, generator=g) * 4 + 2).sort(-1)[0].cuda()
+for _ in range(2):
+    mlp.forward_bf16(net, R, S, rays, z)
+torch.cuda.synchronize()
+buf = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
+_lib.load().nerfb_set_trace(buf.data_ptr())
+mlp.forward_bf16(net, R, S, rays, z)
+torch.cuda.synchronize()
+_lib.load().nerfb_set_trace(None)
+b = buf.cpu().numpy().reshape(3, 4096)
+ev = []
+for region, name in enumerate(("LOAD", "MMA", "EPI")):
+    for v in b[region]:
+        if v == 0: continue
+        ev.append((int(v) & ((1 << 44) - 1), name, int(v) >> 44))
+ev.sort()
+t0 = ev[0][0]
+# print iterations 2..3 (steady state): find MMA op 0 act-wait events
+starts = [t for t, n, tag in ev if n == "MMA" and tag == 0x300]
+lo, hi = starts[2], starts[4]
+print("iteration length (cycles):", [starts[i + 1] - starts[i] for i in range(len(starts) - 1)][:8])
+last = {}
+for t, n, tag in ev:
+    if t < lo or t >= hi: continue
+    kind = tag >> 8
+    desc = {1: "load issued q=%d", 3: "act_ready waited op=%d", 5: "weights ready op=%d", 6: "issued+commits op=%d",
+            7: "mma_done waited l,t=%d", 8: "epilogue end l,t=%d", 9: "signalled t=%d"}[kind] % (tag & 0xFF)
+    print(f"{t - lo:8d}  +{t - last.get(n, t):6d}  {n:4s} {desc}")
+    last[n] = t
