@@ -38,6 +38,10 @@ constexpr int kChunkBytes = 16384;             // 128 rows x 64 bf16 (one K chun
 constexpr int kNS = 4;                         // weight ring slots (= one 256x256 layer per CTA)
 constexpr int kThreads = 384;                  // warps: 0 loader, 1 mma, 2 tmem, 3 relay, 4..11 epilogue
 constexpr int kEpiThreads = 256;
+#ifndef NERFB_LOAD_PIECES
+#define NERFB_LOAD_PIECES 4
+#endif
+constexpr int kLoadPieces = NERFB_LOAD_PIECES;   // bulk copies per weight chunk
 
 // packed weight blob: bf16 chunk images, then the fp32 parameter block
 constexpr int kChunkFull = 2 * kChunkBytes;    // N=256 chunk: two CTA halves
@@ -253,8 +257,12 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
           tr(0, 0x100 + q);
           const LoadEnt le = sc.loads[q];
           mbar_arrive_expect_tx(bar(B_FULL + slot), le.bytes);
-          bulk_g2s(sbase + kSmRing + slot * kChunkBytes, a.packed + le.off + (size_t)rank * le.bytes, le.bytes,
-                   bar(B_FULL + slot));
+          // several smaller bulk copies per chunk: more requests in flight -> lower completion latency
+          const uint32_t piece = le.bytes / kLoadPieces;
+#pragma unroll
+          for (int pc = 0; pc < kLoadPieces; ++pc)
+            bulk_g2s(sbase + kSmRing + slot * kChunkBytes + pc * piece,
+                     a.packed + le.off + (size_t)rank * le.bytes + pc * piece, piece, bar(B_FULL + slot));
         }
       }
     }

@@ -1,0 +1,72 @@
+"""Host-side logic of the multi-GPU path with world_size-2 gloo on CPU: ray
+sharding bounds, the tile all-gather of render_sharded (with a stand-in
+render function -- the kernels need a GPU) and the gradient bucket
+all-reduce.  The CUDA kernels themselves are covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def test_shard_bounds_cover_all_rays():
+    from nerf_projects_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 640000, 762048, 32768):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            per = None
+            for r in range(world):
+                lo, hi, per_r = shard_bounds(n, world, r)
+                assert 0 <= lo <= hi <= n and hi - lo <= per_r
+                per = per_r
+                seen += list(range(lo, hi))[:3] + list(range(max(lo, hi - 3), hi))
+            total = sum(shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world))
+            assert total == n and per * world >= n
+
+
+def _fake_render(H, W, K, rays=None, **kw):
+    ro, rd = rays
+    rgb = ro * 2.0 + rd
+    disp = ro[:, 0] + 1.0
+    acc = rd[:, 2] * 3.0
+    return [rgb, disp, acc, {}]
+
+
+def _worker(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nerf_projects_b200 import parallel
+        g = torch.Generator().manual_seed(0)
+        ro, rd = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+        rgb, disp, acc = parallel.render_sharded(_fake_render, 4, 4, None, ro, rd)
+        ok_render = torch.equal(rgb, ro * 2.0 + rd) and torch.equal(disp, ro[:, 0] + 1.0) and torch.equal(acc, rd[:, 2] * 3)
+        # gradient bucket: rank r holds grad = (r+1) * ones -> mean over ranks
+        params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+        for p in params[:2]:
+            p.grad = torch.full_like(p, float(rank + 1))
+        bucket = parallel.GradBucket(params)          # third parameter has no grad -> treated as zero
+        bucket.allreduce_mean()
+        mean = sum(range(1, world + 1)) / world
+        ok_grad = all(torch.allclose(p.grad, torch.full_like(p, mean)) for p in params[:2]) and \
+            torch.equal(params[2].grad, torch.zeros(2, 2))
+        out[rank] = int(ok_render) + 2 * int(ok_grad)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 33])
+def test_render_sharded_and_grad_bucket_gloo_world2(n):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n, out), nprocs=world, join=True)
+    assert dict(out) == {0: 3, 1: 3}
