@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--chunk", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -252,6 +253,28 @@ def main():
         step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
 
+    # ---- extra leg: one optimisation step of train() on a 4096-ray batch per GPU (BASELINE configs[2]/[4]):
+    # fused forward + backward through the kernels + fused Adam, data-parallel all-reduce when world > 1
+    train = None
+    if not args.no_train:
+        kw_tr = dict(kw_train); kw_tr.update(ndc=False, lindisp=False, perturb=1.0, raw_noise_std=1.0)
+        n_batch = 4096 * world
+        gen = torch.Generator(device=dev).manual_seed(0)
+        sel = torch.randint(0, n_rays, (n_batch,), device=dev, generator=gen)
+        b_o, b_d = resident[0][0][sel].contiguous(), resident[0][1][sel].contiguous()
+        target = torch.rand((n_batch, 3), device=dev, generator=gen)
+        bucket = parallel.GradBucket(grad_vars)
+
+        def step_train():
+            parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, H, W, K, b_o, b_d, target,
+                                        chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
+        step_train()
+        tr_steps = 2
+        tr_ms = timed(step_train, tr_steps)
+        train = {"value": n_batch * tr_steps / (tr_ms * 1e-3), "unit": "rays/s", "ms_per_step": tr_ms / tr_steps,
+                 "config": f"{n_batch}-ray batch, 64+128, perturb=1, raw_noise_std=1, MSE(rgb)+MSE(rgb0), Adam; "
+                           "forward bf16 tensor cores, backward fp32 CUDA-core kernels with recompute"}
+
     rays_per_step = n_rays * world
     value = rays_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = rays_per_step * args.steps / (e2e_ms * 1e-3)
@@ -282,6 +305,8 @@ def main():
                          "kernel_share_of_step": tot_ms / total_ms, "launches_timed": len(mlp_times),
                          "whole_step_frac": value * FLOP_PER_RAY / 1e12 / world / peak},
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             n = 2048
             rate, dt, cores = cpu_reference_rate(n, 1, 1)
