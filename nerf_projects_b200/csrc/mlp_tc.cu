@@ -75,6 +75,27 @@ constexpr int kSmOps = kSmTmemSlot + 16;                 // copy of Sched::ops (
 constexpr int kSmemBytes = kSmOps + 84 * 4;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 
+// ---------------------------------------------------- training tile stores
+// Training keeps, per 128-sample tile, bf16 images of every layer input/gradient in HBM in
+// exactly the shared-memory operand layout (64-column panels of 128 rows x 128 B, 128B swizzle):
+// the forward writes them with bulk copies from its activation buffers, the backward chain
+// does the same for the gradients, and the wgrad kernel reads both back as MN-major operands.
+constexpr int kPanel = kChunkBytes;
+constexpr int kFXg = 0;                               // gamma(x)            1 panel
+constexpr int kFH = kPanel;                           // h_l, l=0..7         4 panels each
+constexpr int kFFeat = kFH + 8 * 4 * kPanel;          // feature             4 panels
+constexpr int kFDg = kFFeat + 4 * kPanel;             // gamma(d)            1 panel
+constexpr int kFHv = kFDg + kPanel;                   // hv (views layer)    2 panels
+constexpr int kFwdTileBytes = kFHv + 2 * kPanel;      // 40 panels = 640 KB
+constexpr int kGHv = 0;                               // d hv                2 panels
+constexpr int kGFeat = 2 * kPanel;                    // d feature           4 panels
+constexpr int kGY = 6 * kPanel;                       // dY_l, l=0..7        4 panels each
+constexpr int kBwdTileBytes = kGY + 8 * 4 * kPanel;   // 38 panels = 608 KB
+constexpr int kMaskWords = 72;                        // per sample: ReLU masks, word l*8 + half*4 + batch; hv at 64..67
+constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7^T..L1^T(28)
+constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
+enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2 };
+
 // ------------------------------------------------------------- schedule
 // A static program shared by the three asynchronous roles.  Generated on the
 // host (build_schedule) and passed by value.
@@ -139,6 +160,31 @@ static void build_schedule(bool vd, Sched& s) {
   }
 }
 
+// backward chain: d_hv -> d_feature -> d_h7 -> ... -> d_h0 with transposed weights
+static void build_schedule_bwd(Sched& s) {
+  s.nloads = s.nops = 0;
+  s.nlayers = 9;
+  auto add_load = [&](int id) -> uint8_t {
+    s.loads[s.nloads] = LoadEnt{(uint32_t)id * kChunkFull, (uint32_t)kChunkBytes};
+    return (uint8_t)s.nloads++;
+  };
+  auto add_op = [&](uint8_t load, int tile, int asrc, int flags) {
+    s.ops[s.nops++] = OpEnt{load, (uint8_t)tile, (uint8_t)asrc, (uint8_t)flags};
+  };
+  {  // views^T: K = 128 (two chunks)
+    const uint8_t l0 = add_load(0), l1 = add_load(1);
+    add_op(l0, 0, 0, F_FIRST); add_op(l1, 0, 1, F_LAST);
+    add_op(l0, 1, 0, F_FIRST | F_REL_SLOT); add_op(l1, 1, 1, F_LAST | F_REL_SLOT);
+  }
+  for (int j = 1; j <= 8; ++j) {
+    uint8_t l[4];
+    for (int k = 0; k < 4; ++k) l[k] = add_load(2 + 4 * (j - 1) + k);
+    for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
+    for (int k = 0; k < 4; ++k)
+      add_op(l[k], 1, k, F_REL_SLOT | (k == 0 ? F_FIRST | F_BLOCK4 : 0) | (k == 3 ? F_LAST : 0));
+  }
+}
+
 struct MlpArgs {
   const float* rays; int rw;
   const float* z; const float* pts; const float* viewdirs;
@@ -147,6 +193,11 @@ struct MlpArgs {
   int nst, nclusters;
   Watch watch;
   long long* trace;   // debug timeline (nerfb_set_trace), 3 regions of kTraceLen entries
+  uint8_t* acts;      // MODE_FWD_SAVE: [ntiles][kFwdTileBytes]
+  uint32_t* masks;    // MODE_FWD_SAVE (out) / MODE_BWD (in): [ntiles*128][kMaskWords]
+  uint8_t* gstore;    // MODE_BWD: [ntiles][kBwdTileBytes]
+  const float* d_raw; // MODE_BWD: [nrows,4]
+  int param_off;      // byte offset of the fp32 parameter block inside `packed`
 };
 constexpr int kTraceLen = 4096;
 static long long* g_trace = nullptr;
@@ -192,8 +243,11 @@ __device__ __forceinline__ void store_row32(uint8_t* chunk, int row, int unit0, 
 }
 
 // -------------------------------------------------------------- kernel
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc) {
+nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc) {
+  constexpr bool SAVE = (MODE == MODE_FWD_SAVE);
+  constexpr bool BWD = (MODE == MODE_BWD);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -232,7 +286,7 @@ nerf_mlp_fwd_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ S
         (uint32_t)e.load | ((uint32_t)e.tile << 8) | ((uint32_t)e.asrc << 16) | ((uint32_t)e.flags << 24);
   }
   {
-    const float* gpar = reinterpret_cast<const float*>(a.packed + (a.use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD));
+    const float* gpar = reinterpret_cast<const float*>(a.packed + a.param_off);
     for (int i = tid; i < kParamFloats; i += kThreads) s_par[i] = __ldg(gpar + i);
   }
   if (warp == 2) {
@@ -708,7 +762,7 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
   }
   static bool attr_set = false;
   if (!attr_set) {
-    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   MlpArgs a{};
@@ -721,11 +775,12 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
   a.watch = get_watch();
   a.trace = g_trace;
   a.out_ch = use_viewdirs ? 4 : out_ch;
+  a.param_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * a.nclusters);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
-  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_kernel, a, use_viewdirs ? sched_vd : sched_novd));
+  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, use_viewdirs ? sched_vd : sched_novd));
   return check_launch("nerf_mlp_fwd_kernel");
 }

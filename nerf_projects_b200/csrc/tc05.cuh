@@ -136,6 +136,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -272,6 +282,25 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
 }
 // advance along K inside the 128-byte swizzle atom: +32 B per UMMA_K=16 bf16
 __device__ __forceinline__ uint64_t sdesc_advance_k(uint64_t d, int k16) { return d + (uint64_t)(k16 * 2); }
+
+// MN-major operand (the contraction index K runs over the ROWS of the stored tile): the same
+// physical image -- rows of 128 B (64 bf16 along M/N), 8-row groups 1024 B apart, 128B swizzle --
+// read "transposed".  LBO = byte stride between 64-element M/N panels, SBO = 1024 (8 K-rows).
+// A K=16 step advances the start address by 16 rows = 2048 B.
+__device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t smem_addr, uint32_t panel_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((panel_stride_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset
+  d |= (uint64_t)(1024 >> 4) << 32;                            // stride byte offset
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor with both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
 
 // instruction descriptor: kind::f16, A/B = bf16 K-major, D = fp32
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {

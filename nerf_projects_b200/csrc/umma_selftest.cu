@@ -101,9 +101,86 @@ umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __r
   if (warp == 0) tmem_dealloc<CG>(tmem_base, ncols);
 }
 
+// MN-major self-test (the wgrad operand form): C[128,N] = At^T Bt with At [K,128] and Bt [K,N]
+// row-major, staged as [K rows x 64-col panels] swizzled images, K multiple of 16 (<= 128).
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_mn_kernel(int N, int K, const float* __restrict__ At, const float* __restrict__ Bt,
+                        float* __restrict__ C, Watch watch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int panel_bytes = 128 * 128;              // panels are laid out as 128-row tiles (like the act images)
+  uint8_t* sA = smem;                             // 2 panels (M = 128)
+  uint8_t* sB = smem + 2 * panel_bytes;           // N/64 panels
+  // stage: element (k, m) of At -> panel m/64, row k, col m%64
+  for (int idx = tid; idx < 128 * (128 / 8); idx += 128) {
+    const int k = idx / 16, u = idx % 16;         // u: 16-byte unit along M (8 elements)
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (k < K) {
+      const float* s = At + (size_t)k * 128 + u * 8;
+      v = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+    }
+    *reinterpret_cast<uint4*>(sA + (u / 8) * panel_bytes + sw128_offset(k, u % 8)) = v;
+  }
+  for (int idx = tid; idx < 128 * (N / 8); idx += 128) {
+    const int k = idx / (N / 8), u = idx % (N / 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (k < K) {
+      const float* s = Bt + (size_t)k * N + u * 8;
+      v = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+    }
+    *reinterpret_cast<uint4*>(sB + (u / 8) * panel_bytes + sw128_offset(k, u % 8)) = v;
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) { mbar_init(smem_u32(&bar_done), 1); fence_barrier_init(); }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) { tmem_alloc<1>(smem_u32(&tmem_base_slot), ncols); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_bf16_mn(128, N);
+    const uint64_t da = make_sdesc_sw128_mn(smem_u32(sA), panel_bytes);
+    const uint64_t db = make_sdesc_sw128_mn(smem_u32(sB), panel_bytes);
+    if (elect_one()) {
+      for (int k = 0; k < K / 16; ++k)
+        umma_bf16<1>(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k ? 1u : 0u);
+      umma_commit<1>(smem_u32(&bar_done));
+    }
+    __syncwarp();
+  }
+  mbar_wait(smem_u32(&bar_done), 0, watch, 2);
+  tc_fence_after();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) C[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_base, ncols);
+}
+
 }  // namespace nerfb
 
 using namespace nerfb;
+
+extern "C" int nerfb_umma_selftest_mn(int N, int K, const float* At, const float* Bt, float* C, void* stream) {
+  NERFB_REQUIRE(N >= 64 && N <= 256 && N % 64 == 0 && K >= 16 && K <= 128 && K % 16 == 0 && At && Bt && C,
+                "nerfb_umma_selftest_mn: bad arguments (N=%d K=%d)", N, K);
+  const size_t smem = (size_t)(2 + N / 64) * 128 * 128 + 1024;
+  tc05::Watch w = get_watch();
+  NERFB_CUDA(cudaFuncSetAttribute(umma_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_mn_kernel<<<1, 128, smem, as_stream(stream)>>>(N, K, At, Bt, C, w);
+  return check_launch("umma_selftest_mn_kernel");
+}
 
 extern "C" const unsigned long long* nerfb_watchdog_record(void) {
   get_watch();

@@ -266,6 +266,16 @@ def umma_selftest(A, B, cta_group=1):
     return Cm
 
 
+def umma_selftest_mn(At, Bt):
+    K, N = Bt.shape
+    assert At.shape == (K, 128)
+    Cm = _empty((128, N), At)
+    L.check(L.load().nerfb_umma_selftest_mn(N, K, L.ptr(At), L.ptr(Bt), L.ptr(Cm), L.stream()),
+            "nerfb_umma_selftest_mn")
+    _count()
+    return Cm
+
+
 # ------------------------------------------------------------ optimiser
 
 def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):

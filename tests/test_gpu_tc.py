@@ -35,6 +35,24 @@ def test_umma_selftest(cg, N, K):
     assert err < 1e-3, f"max err {err}"
 
 
+@pytest.mark.parametrize("N,K", [(256, 128), (128, 64), (64, 16), (256, 48)])
+def test_umma_selftest_mn_major(N, K):
+    """MN-major operands (contraction over the rows of the stored tiles) -- the wgrad form."""
+    from nerf_projects_b200 import ops, _lib
+    gen = torch.Generator().manual_seed(N + K)
+    At = torch.randn(K, 128, generator=gen)
+    Bt = torch.randn(K, N, generator=gen)
+    try:
+        C = ops.umma_selftest_mn(At.to(DEV), Bt.to(DEV))
+        torch.cuda.synchronize()
+    except Exception:
+        print("watchdog:", _lib.watchdog_record())
+        raise
+    ref = bf16r(At).double().T @ bf16r(Bt).double()
+    err = (C.cpu().double() - ref).abs().max().item()
+    assert err < 1e-3, f"max err {err}"
+
+
 def _net(params, use_viewdirs, out_ch):
     import nerf_projects_b200 as nb
     m = nb.NeRF(8, 256, 63, 27 if use_viewdirs else 0, out_ch, [4], use_viewdirs).to(DEV)
