@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libnerf_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
 SOURCES = ["api.cu", "rays.cu", "embed.cu", "linear_fp32.cu", "composite.cu", "sample_pdf.cu", "adam.cu",
-           "umma_selftest.cu", "mlp_tc.cu"]
+           "umma_selftest.cu", "mlp_tc.cu", "wgrad_tc.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

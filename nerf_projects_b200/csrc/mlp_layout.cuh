@@ -1,0 +1,73 @@
+// Geometry, packed-weight layout and the training tile stores shared by the fused MLP
+// kernels (mlp_tc.cu) and the weight-gradient kernel (wgrad_tc.cu).
+#pragma once
+#include <cstdint>
+
+namespace nerfb {
+
+// ------------------------------------------------------------ geometry
+constexpr int kTileRows = 128;                 // rows per CTA per tile (UMMA M / 2)
+constexpr int kSuperRows = 512;                // rows per cluster per iteration (2 CTAs x 2 tiles)
+constexpr int kChunkBytes = 16384;             // 128 rows x 64 bf16 (one K chunk of A, or half of a B chunk)
+constexpr int kNS = 4;                         // weight ring slots (= one 256x256 layer per CTA)
+constexpr int kThreads = 384;                  // warps: 0 loader, 1 mma, 2 tmem, 3 relay, 4..11 epilogue
+constexpr int kEpiThreads = 256;
+#ifndef NERFB_LOAD_PIECES
+#define NERFB_LOAD_PIECES 4
+#endif
+constexpr int kLoadPieces = NERFB_LOAD_PIECES;   // bulk copies per weight chunk
+
+// packed weight blob: bf16 chunk images, then the fp32 parameter block
+constexpr int kChunkFull = 2 * kChunkBytes;    // N=256 chunk: two CTA halves
+constexpr int kChunkViews = kChunkBytes;       // N=128 chunk: two halves of 64 rows
+constexpr int kNumFullChunks = 34;             // L0(1) L1-4(16) L5(1+4) L6-7(8) FEAT(4)
+constexpr int kNumViewChunks = 5;              // gamma(d) part + 4 feature parts
+constexpr int kChunkAreaVD = kNumFullChunks * kChunkFull + kNumViewChunks * kChunkViews;
+constexpr int kChunkAreaNoVD = 30 * kChunkFull;
+
+// fp32 parameter block (floats)
+constexpr int kOffBias = 0;                    // 8 x 256 pts biases
+constexpr int kOffBiasFeat = 2048;             // 256
+constexpr int kOffBiasViews = 2304;            // 128
+constexpr int kOffHeadW = 2432;                // 5 x 256: alpha_linear.weight (row 0) or output_linear.weight
+constexpr int kOffRgbW = 3712;                 // 3 x 128
+constexpr int kOffHeadB = 4096;                // 8
+constexpr int kOffRgbB = 4104;                 // 4
+constexpr int kParamFloats = 4108;
+constexpr int kParamBytes = kParamFloats * 4;  // 16432
+
+// shared memory map (bytes from the 1024-aligned dynamic smem base)
+constexpr int kSmAct = 0;                      // 2 tiles x 4 chunks
+constexpr int kSmEnc = 2 * 4 * kChunkBytes;    // 131072: gamma(x) / gamma(d) operand chunk
+constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
+constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
+constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
+constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
+constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
+constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
+constexpr int kSmOps = kSmTmemSlot + 16;                 // copy of Sched::ops (u32 each)
+constexpr int kSmemBytes = kSmOps + 84 * 4;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+
+// ---------------------------------------------------- training tile stores
+// Training keeps, per 128-sample tile, bf16 images of every layer input/gradient in HBM in
+// exactly the shared-memory operand layout (64-column panels of 128 rows x 128 B, 128B swizzle):
+// the forward writes them with bulk copies from its activation buffers, the backward chain
+// does the same for the gradients, and the wgrad kernel reads both back as MN-major operands.
+constexpr int kPanel = kChunkBytes;
+constexpr int kFXg = 0;                               // gamma(x)            1 panel
+constexpr int kFH = kPanel;                           // h_l, l=0..7         4 panels each
+constexpr int kFFeat = kFH + 8 * 4 * kPanel;          // feature             4 panels
+constexpr int kFDg = kFFeat + 4 * kPanel;             // gamma(d)            1 panel
+constexpr int kFHv = kFDg + kPanel;                   // hv (views layer)    2 panels
+constexpr int kFwdTileBytes = kFHv + 2 * kPanel;      // 40 panels = 640 KB
+constexpr int kGHv = 0;                               // d hv                2 panels
+constexpr int kGFeat = 2 * kPanel;                    // d feature           4 panels
+constexpr int kGY = 6 * kPanel;                       // dY_l, l=0..7        4 panels each
+constexpr int kBwdTileBytes = kGY + 8 * 4 * kPanel;   // 38 panels = 608 KB
+constexpr int kMaskWords = 72;                        // per sample: ReLU masks, word l*8 + half*4 + batch; hv at 64..67
+constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7^T..L1^T(28)
+constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
+enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2 };
+
+}  // namespace nerfb

@@ -25,76 +25,12 @@
 //   * every barrier wait is bounded by a watchdog (tc05.cuh).
 #include "common.cuh"
 #include "tc05.cuh"
+#include "mlp_layout.cuh"
 
 namespace nerfb {
 using namespace tc05;
 
 tc05::Watch get_watch();  // umma_selftest.cu
-
-// ------------------------------------------------------------ geometry
-constexpr int kTileRows = 128;                 // rows per CTA per tile (UMMA M / 2)
-constexpr int kSuperRows = 512;                // rows per cluster per iteration (2 CTAs x 2 tiles)
-constexpr int kChunkBytes = 16384;             // 128 rows x 64 bf16 (one K chunk of A, or half of a B chunk)
-constexpr int kNS = 4;                         // weight ring slots (= one 256x256 layer per CTA)
-constexpr int kThreads = 384;                  // warps: 0 loader, 1 mma, 2 tmem, 3 relay, 4..11 epilogue
-constexpr int kEpiThreads = 256;
-#ifndef NERFB_LOAD_PIECES
-#define NERFB_LOAD_PIECES 4
-#endif
-constexpr int kLoadPieces = NERFB_LOAD_PIECES;   // bulk copies per weight chunk
-
-// packed weight blob: bf16 chunk images, then the fp32 parameter block
-constexpr int kChunkFull = 2 * kChunkBytes;    // N=256 chunk: two CTA halves
-constexpr int kChunkViews = kChunkBytes;       // N=128 chunk: two halves of 64 rows
-constexpr int kNumFullChunks = 34;             // L0(1) L1-4(16) L5(1+4) L6-7(8) FEAT(4)
-constexpr int kNumViewChunks = 5;              // gamma(d) part + 4 feature parts
-constexpr int kChunkAreaVD = kNumFullChunks * kChunkFull + kNumViewChunks * kChunkViews;
-constexpr int kChunkAreaNoVD = 30 * kChunkFull;
-
-// fp32 parameter block (floats)
-constexpr int kOffBias = 0;                    // 8 x 256 pts biases
-constexpr int kOffBiasFeat = 2048;             // 256
-constexpr int kOffBiasViews = 2304;            // 128
-constexpr int kOffHeadW = 2432;                // 5 x 256: alpha_linear.weight (row 0) or output_linear.weight
-constexpr int kOffRgbW = 3712;                 // 3 x 128
-constexpr int kOffHeadB = 4096;                // 8
-constexpr int kOffRgbB = 4104;                 // 4
-constexpr int kParamFloats = 4108;
-constexpr int kParamBytes = kParamFloats * 4;  // 16432
-
-// shared memory map (bytes from the 1024-aligned dynamic smem base)
-constexpr int kSmAct = 0;                      // 2 tiles x 4 chunks
-constexpr int kSmEnc = 2 * 4 * kChunkBytes;    // 131072: gamma(x) / gamma(d) operand chunk
-constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
-constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
-constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
-constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
-constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
-constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
-constexpr int kSmOps = kSmTmemSlot + 16;                 // copy of Sched::ops (u32 each)
-constexpr int kSmemBytes = kSmOps + 84 * 4;
-static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
-
-// ---------------------------------------------------- training tile stores
-// Training keeps, per 128-sample tile, bf16 images of every layer input/gradient in HBM in
-// exactly the shared-memory operand layout (64-column panels of 128 rows x 128 B, 128B swizzle):
-// the forward writes them with bulk copies from its activation buffers, the backward chain
-// does the same for the gradients, and the wgrad kernel reads both back as MN-major operands.
-constexpr int kPanel = kChunkBytes;
-constexpr int kFXg = 0;                               // gamma(x)            1 panel
-constexpr int kFH = kPanel;                           // h_l, l=0..7         4 panels each
-constexpr int kFFeat = kFH + 8 * 4 * kPanel;          // feature             4 panels
-constexpr int kFDg = kFFeat + 4 * kPanel;             // gamma(d)            1 panel
-constexpr int kFHv = kFDg + kPanel;                   // hv (views layer)    2 panels
-constexpr int kFwdTileBytes = kFHv + 2 * kPanel;      // 40 panels = 640 KB
-constexpr int kGHv = 0;                               // d hv                2 panels
-constexpr int kGFeat = 2 * kPanel;                    // d feature           4 panels
-constexpr int kGY = 6 * kPanel;                       // dY_l, l=0..7        4 panels each
-constexpr int kBwdTileBytes = kGY + 8 * 4 * kPanel;   // 38 panels = 608 KB
-constexpr int kMaskWords = 72;                        // per sample: ReLU masks, word l*8 + half*4 + batch; hv at 64..67
-constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7^T..L1^T(28)
-constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
-enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2 };
 
 // ------------------------------------------------------------- schedule
 // A static program shared by the three asynchronous roles.  Generated on the
@@ -193,8 +129,7 @@ struct MlpArgs {
   int nst, nclusters;
   Watch watch;
   long long* trace;   // debug timeline (nerfb_set_trace), 3 regions of kTraceLen entries
-  uint8_t* acts;      // MODE_FWD_SAVE: [ntiles][kFwdTileBytes]
-  uint32_t* masks;    // MODE_FWD_SAVE (out) / MODE_BWD (in): [ntiles*128][kMaskWords]
+  uint8_t* acts;      // MODE_FWD_SAVE (out) / MODE_BWD (in, ReLU masks): [ntiles][kFwdTileBytes]
   uint8_t* gstore;    // MODE_BWD: [ntiles][kBwdTileBytes]
   const float* d_raw; // MODE_BWD: [nrows,4]
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
@@ -444,12 +379,25 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       if (enc_cnt > 0) mbar_wait(bar(B_ENC), (enc_cnt - 1) & 1, a.watch, 0x600 + enc_cnt);
       ++enc_cnt;
     };
-    auto signal_ready = [&](int t) {
+    // Publish tile t's freshly written operand chunks: make them visible to the async proxy,
+    // (optionally) tell the MMA issuer, and -- training modes -- bulk-store `npanels` panels of
+    // act_t to `gdst`.  The pre-barrier wait covers the PREVIOUS bulk store (other tile, issued a
+    // whole epilogue ago), so after the barrier every thread may overwrite that tile's buffer.
+    auto publish = [&](int t, bool signal, uint8_t* gdst, int npanels) {
       tc_fence_before();
       fence_proxy_async_smem();
+      if ((SAVE || BWD) && et == 0) bulk_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et == 0) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
+      if (et == 0) {
+        if (signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
+        if ((SAVE || BWD) && gdst != nullptr) {
+          for (int pnl = 0; pnl < npanels; ++pnl)
+            bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
+          bulk_commit();
+        }
+      }
     };
+    auto signal_ready = [&](int t) { publish(t, true, nullptr, 0); };
     // sample position of my row in tile t
     auto load_point = [&](long long grow, float (&p)[3]) {
       p[0] = p[1] = p[2] = 0.f;
@@ -473,29 +421,39 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         p[0] = __ldg(src); p[1] = __ldg(src + 1); p[2] = __ldg(src + 2);
       }
     };
-    auto write_enc_x = [&](long long grow) {
+    // gsave != nullptr (MODE_FWD_SAVE): also write my half row of the panel image to global
+    auto write_enc_x = [&](long long grow, uint8_t* gsave) {
       float p[3];
       load_point(grow, p);
       uint32_t w[16];
       if (hh == 0) encode_cols<10, 0>(p, w); else encode_cols<10, 1>(p, w);
       store_row32(smem + kSmEnc, row, 4 * hh, w);
+      if (SAVE && gsave != nullptr) store_row32(gsave, row, 4 * hh, w);
     };
-    auto write_enc_d = [&](long long grow) {
+    auto write_enc_d = [&](long long grow, uint8_t* gsave) {
       float p[3];
       load_dir(grow, p);
       uint32_t w[16];
       if (hh == 0) encode_cols<4, 0>(p, w); else encode_cols<4, 1>(p, w);
       store_row32(smem + kSmEnc, row, 4 * hh, w);
+      if (SAVE && gsave != nullptr) store_row32(gsave, row, 4 * hh, w);
     };
 
+    if constexpr (!BWD) {
     for (int it = 0; it < niter; ++it) {
       const long long st = cluster_id + (long long)it * a.nclusters;
       long long grow[2];
       grow[0] = st * kSuperRows + rank * kTileRows + row;
       grow[1] = grow[0] + 2 * kTileRows;
+      // global 128-row tile index of (tile t, this CTA) and its training store
+      uint8_t* gtile[2] = {nullptr, nullptr};
+      if (SAVE) {
+        gtile[0] = a.acts + (size_t)(st * 4 + rank) * kFwdTileBytes;
+        gtile[1] = a.acts + (size_t)(st * 4 + 2 + rank) * kFwdTileBytes;
+      }
       for (int t = 0; t < 2; ++t) {       // layer-0 operands
         enc_wait();
-        write_enc_x(grow[t]);
+        write_enc_x(grow[t], SAVE ? gtile[t] + kFXg : nullptr);
         signal_ready(t);
       }
       for (int l = 0; l < sc.nlayers; ++l) {
@@ -585,12 +543,21 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 uint32_t v[32];
                 tmem_ld32(taddr + 32 * b, v);
                 tmem_ld_wait();
+                float xs[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   const float x = fmaxf(__uint_as_float(v[j]) + bias[32 * b + j], 0.f);
+                  xs[j] = x;
                   c0 = fmaf(x, rw[32 * b + j], c0);
                   c1 = fmaf(x, rw[128 + 32 * b + j], c1);
                   c2 = fmaf(x, rw[256 + 32 * b + j], c2);
+                }
+                if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients
+                  uint32_t w[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(xs[2 * i], xs[2 * i + 1]);
+                  const int col0 = 32 * b;
+                  store_row32(gtile[t] + kFHv + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
                 }
               }
               if (grow[t] < a.nrows) {
@@ -601,14 +568,124 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             }
           }
           // ---- operands the NEXT layer needs besides the activations
-          if (l == 4) { enc_wait(); write_enc_x(grow[t]); }
-          if (l == 8) { enc_wait(); write_enc_d(grow[t]); }
+          if (l == 4) { enc_wait(); write_enc_x(grow[t], nullptr); }
+          if (l == 8) { enc_wait(); write_enc_d(grow[t], SAVE ? gtile[t] + kFDg : nullptr); }
           if (et == 0) tr(2, 0x800 + l * 2 + t);
-          if (l + 1 < sc.nlayers) signal_ready(t);
-          else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+          if (l + 1 < sc.nlayers) {
+            // training: h_l (l < 8) / feature (l == 8) go to the tile store as written
+            uint8_t* gdst = nullptr;
+            if (SAVE) gdst = gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat);
+            publish(t, true, gdst, 4);
+          } else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
         }
       }
     }
+    } else {
+      // ================= MODE_BWD: data-gradient chain  d_raw -> d_hv -> d_feature -> dY_7 .. dY_0
+      // Layer j of the schedule multiplies by a transposed weight matrix; its epilogue applies the
+      // ReLU mask of the layer it lands on (read from the forward tile store), writes the bf16
+      // gradient as the next A operand and bulk-stores it for the weight-gradient kernel.
+      const float* w_rgb = s_par + kOffRgbW;
+      const float* w_alpha = s_par + kOffHeadW;
+      for (int it = 0; it < niter; ++it) {
+        const long long st = cluster_id + (long long)it * a.nclusters;
+        long long grow[2];
+        grow[0] = st * kSuperRows + rank * kTileRows + row;
+        grow[1] = grow[0] + 2 * kTileRows;
+        const uint8_t* ftile[2];
+        uint8_t* gtile[2];
+        for (int t = 0; t < 2; ++t) {
+          const size_t T = (size_t)(st * 4 + 2 * t + rank);
+          ftile[t] = a.acts + T * kFwdTileBytes;
+          gtile[t] = a.gstore + T * kBwdTileBytes;
+        }
+        float dsig[2];
+        for (int t = 0; t < 2; ++t) {
+          // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
+          float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow[t] < a.nrows) dr = __ldg(reinterpret_cast<const float4*>(a.d_raw) + grow[t]);
+          dsig[t] = dr.w;
+          uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
+          const uint8_t* hvp = ftile[t] + kFHv + hh * kPanel;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t off = sw128_offset(row, u);
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(hvp + off));
+            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = 64 * hh + 8 * u + 2 * i;
+              const float g0 = fmaf(dr.z, w_rgb[256 + c], fmaf(dr.y, w_rgb[128 + c], dr.x * w_rgb[c]));
+              const float g1 = fmaf(dr.z, w_rgb[257 + c], fmaf(dr.y, w_rgb[129 + c], dr.x * w_rgb[c + 1]));
+              o[i] = pack_bf16x2(g0, g1) & bf16x2_nonzero_mask(mm[i]);
+            }
+            *reinterpret_cast<uint4*>(act_t + hh * kChunkBytes + off) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          publish(t, true, gtile[t] + kGHv, 2);
+        }
+        for (int j = 0; j < sc.nlayers; ++j) {
+          // masks come from h_m (bf16, post-ReLU) of the layer the gradient lands on
+          const int m = 8 - j;                       // j=1 -> h7 ... j=8 -> h0 ; j=0: feature (no ReLU)
+          for (int t = 0; t < 2; ++t) {
+            const uint8_t* hsrc = ftile[t] + kFH + (m < 0 ? 0 : m) * 4 * kPanel;
+            const int colbase = 128 * hh;
+            uint4 hm[2][4];
+            auto load_mask = [&](int b, uint4 (&dst)[4]) {
+              const int col0 = colbase + 32 * b;
+              const uint8_t* pp = hsrc + (col0 >> 6) * kPanel;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                dst[i] = __ldg(reinterpret_cast<const uint4*>(pp + sw128_offset(row, ((col0 & 63) >> 3) + i)));
+            };
+            if (j > 0) { load_mask(0, hm[0]); load_mask(1, hm[1]); }
+            mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
+            done_cnt[t]++;
+            if (et == 0) tr(2, 0x700 + j * 2 + t);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + lane_addr + t * 256;
+            uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
+            const float ds = dsig[t];
+            uint32_t v[2][32];
+            tmem_ld32(taddr + colbase, v[0]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              tmem_ld_wait();
+              if (b < 3) tmem_ld32(taddr + colbase + 32 * (b + 1), v[(b + 1) & 1]);
+              const uint32_t (&vv)[32] = v[b & 1];
+              uint32_t w[16];
+              if (j == 1) {
+                const float* wa = w_alpha + colbase + 32 * b;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  w[i] = pack_bf16x2(fmaf(ds, wa[2 * i], __uint_as_float(vv[2 * i])),
+                                     fmaf(ds, wa[2 * i + 1], __uint_as_float(vv[2 * i + 1])));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1]));
+              }
+              if (j > 0) {
+                const uint4 (&mk)[4] = hm[b & 1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  w[4 * i + 0] &= bf16x2_nonzero_mask(mk[i].x);
+                  w[4 * i + 1] &= bf16x2_nonzero_mask(mk[i].y);
+                  w[4 * i + 2] &= bf16x2_nonzero_mask(mk[i].z);
+                  w[4 * i + 3] &= bf16x2_nonzero_mask(mk[i].w);
+                }
+                if (b < 2) load_mask(b + 2, hm[b & 1]);
+              }
+              const int col0 = colbase + 32 * b;
+              store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+            }
+            if (et == 0) tr(2, 0x800 + j * 2 + t);
+            uint8_t* gdst = gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);
+            publish(t, j + 1 < sc.nlayers, gdst, 4);
+          }
+        }
+      }
+    }
+    if ((SAVE || BWD) && et == 0) bulk_wait0();
   }
 
   // ---- teardown
@@ -632,6 +709,33 @@ struct PackArgs {
   const float* bias[10];
 };
 
+__device__ void fill_param_block(const PackArgs& pa, float* par) {
+  for (int i = threadIdx.x; i < kParamFloats; i += blockDim.x) {
+    float v = 0.f;
+    if (i < kOffBiasFeat) {
+      v = pa.bias[i >> 8][i & 255];
+    } else if (i < kOffBiasViews) {
+      if (pa.use_viewdirs) v = pa.bias[8][i - kOffBiasFeat];
+    } else if (i < kOffHeadW) {
+      if (pa.use_viewdirs) v = pa.bias[9][i - kOffBiasViews];
+    } else if (i < kOffRgbW) {
+      const int j = i - kOffHeadW;              // head weights [k][256]
+      const int rows = pa.use_viewdirs ? 1 : pa.out_ch;
+      if (j < rows * 256) v = pa.src[0][j];
+    } else if (i < kOffHeadB) {
+      if (pa.use_viewdirs) v = pa.src[2][i - kOffRgbW];   // rgb_linear.weight [3,128]
+    } else if (i < kOffRgbB) {
+      const int j = i - kOffHeadB;
+      const int rows = pa.use_viewdirs ? 1 : pa.out_ch;
+      if (j < rows) v = pa.src[1][j];
+    } else {
+      const int j = i - kOffRgbB;
+      if (pa.use_viewdirs && j < 3) v = pa.src[3][j];
+    }
+    par[i] = v;
+  }
+}
+
 __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, uint8_t* __restrict__ blob, int chunk_area) {
   const int c = blockIdx.y;
   if (c < pa.nchunks) {
@@ -652,32 +756,32 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, uint8_t
       *reinterpret_cast<uint4*>(blob + pc.off + (size_t)half * half_rows * 128 + sw128_offset(r, u)) = v;
     }
   } else if (blockIdx.x == 0) {
-    // fp32 parameter block
-    float* par = reinterpret_cast<float*>(blob + chunk_area);
-    for (int i = threadIdx.x; i < kParamFloats; i += blockDim.x) {
-      float v = 0.f;
-      if (i < kOffBiasFeat) {
-        v = pa.bias[i >> 8][i & 255];
-      } else if (i < kOffBiasViews) {
-        if (pa.use_viewdirs) v = pa.bias[8][i - kOffBiasFeat];
-      } else if (i < kOffHeadW) {
-        if (pa.use_viewdirs) v = pa.bias[9][i - kOffBiasViews];
-      } else if (i < kOffRgbW) {
-        const int j = i - kOffHeadW;              // head weights [k][256]
-        const int rows = pa.use_viewdirs ? 1 : pa.out_ch;
-        if (j < rows * 256) v = pa.src[0][j];
-      } else if (i < kOffHeadB) {
-        if (pa.use_viewdirs) v = pa.src[2][i - kOffRgbW];   // rgb_linear.weight [3,128]
-      } else if (i < kOffRgbB) {
-        const int j = i - kOffHeadB;
-        const int rows = pa.use_viewdirs ? 1 : pa.out_ch;
-        if (j < rows) v = pa.src[1][j];
-      } else {
-        const int j = i - kOffRgbB;
-        if (pa.use_viewdirs && j < 3) v = pa.src[3][j];
-      }
-      par[i] = v;
+    fill_param_block(pa, reinterpret_cast<float*>(blob + chunk_area));
+  }
+}
+
+// Transposed weight images for the data-gradient chain: chunk = B operand [n = 256 rows (two CTA
+// halves), k = 64 columns] with B[n][k] = W[(row0 + k) * ld + col0 + n]  (i.e. W^T).
+struct PackChunkT { const float* w; int ld, row0, col0; };
+struct PackArgsT { PackChunkT ch[kNumBwdChunks]; };
+
+__global__ void pack_weights_bwd_kernel(const __grid_constant__ PackArgsT pt, const __grid_constant__ PackArgs pa,
+                                        uint8_t* __restrict__ blob) {
+  const int c = blockIdx.y;
+  if (c < kNumBwdChunks) {
+    const PackChunkT pc = pt.ch[c];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 256 * 8; idx += gridDim.x * blockDim.x) {
+      const int n = idx & 255, u = idx >> 8;       // n fastest: coalesced reads along a weight row
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __ldg(pc.w + (size_t)(pc.row0 + 8 * u + j) * pc.ld + pc.col0 + n);
+      const uint4 v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                 pack_bf16x2(f[6], f[7]));
+      *reinterpret_cast<uint4*>(blob + (size_t)c * kChunkFull + (size_t)(n >> 7) * kChunkBytes +
+                                sw128_offset(n & 127, u)) = v;
     }
+  } else if (blockIdx.x == 0) {
+    fill_param_block(pa, reinterpret_cast<float*>(blob + kChunkAreaBwd));
   }
 }
 
@@ -744,6 +848,39 @@ extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs
   return check_launch("pack_weights_kernel");
 }
 
+static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
+  static Sched sched_vd, sched_novd, sched_bwd;
+  static bool init = false;
+  if (!init) {
+    build_schedule(true, sched_vd);
+    build_schedule(false, sched_novd);
+    build_schedule_bwd(sched_bwd);
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    init = true;
+  }
+  a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
+  a.nclusters = sm_count() / 2;
+  if (a.nclusters > a.nst) a.nclusters = a.nst;
+  a.watch = get_watch();
+  a.trace = g_trace;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * a.nclusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = as_stream(stream);
+  if (mode == MODE_FWD) {
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd));
+    return check_launch("nerf_mlp_kernel<FWD>");
+  } else if (mode == MODE_FWD_SAVE) {
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd));
+    return check_launch("nerf_mlp_kernel<FWD_SAVE>");
+  }
+  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd));
+  return check_launch("nerf_mlp_kernel<BWD>");
+}
+
 extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const float* z, const float* pts,
                                   const float* viewdirs, int use_viewdirs, int out_ch, const void* packed, float* raw,
                                   void* stream) {
@@ -753,34 +890,77 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
   NERFB_REQUIRE(!use_viewdirs || viewdirs || (rays && ray_width >= 11),
                 "nerfb_mlp_fwd_bf16: view directions requested but not provided");
   if (R == 0) return NERFB_OK;
-  static Sched sched_vd, sched_novd;
-  static bool sched_init = false;
-  if (!sched_init) {
-    build_schedule(true, sched_vd);
-    build_schedule(false, sched_novd);
-    sched_init = true;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
   MlpArgs a{};
   a.rays = rays; a.rw = ray_width; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
   a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = use_viewdirs;
   a.packed = (const uint8_t*)packed; a.raw = raw;
-  a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
-  a.nclusters = sm_count() / 2;
-  if (a.nclusters > a.nst) a.nclusters = a.nst;
-  a.watch = get_watch();
-  a.trace = g_trace;
   a.out_ch = use_viewdirs ? 4 : out_ch;
   a.param_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * a.nclusters);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = as_stream(stream);
-  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, use_viewdirs ? sched_vd : sched_novd));
-  return check_launch("nerf_mlp_fwd_kernel");
+  return launch_mlp(MODE_FWD, a, use_viewdirs != 0, stream);
+}
+
+extern "C" size_t nerfb_train_store_bytes(long long nrows, int which) {
+  const long long ntiles = 4 * ((nrows + kSuperRows - 1) / kSuperRows);
+  return (size_t)ntiles * (size_t)(which == 0 ? kFwdTileBytes : kBwdTileBytes);
+}
+
+extern "C" int nerfb_mlp_fwd_save_bf16(int R, int S, const float* rays, int ray_width, const float* z,
+                                       const float* pts, const float* viewdirs, const void* packed, float* raw,
+                                       void* acts, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw && acts, "nerfb_mlp_fwd_save_bf16: bad arguments");
+  NERFB_REQUIRE(pts || (rays && z && ray_width >= 8), "nerfb_mlp_fwd_save_bf16: need pts or rays+z");
+  NERFB_REQUIRE(viewdirs || (rays && ray_width >= 11), "nerfb_mlp_fwd_save_bf16: view directions not provided");
+  if (R == 0) return NERFB_OK;
+  MlpArgs a{};
+  a.rays = rays; a.rw = ray_width; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
+  a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = 1;
+  a.packed = (const uint8_t*)packed; a.raw = raw; a.out_ch = 4;
+  a.param_off = kChunkAreaVD;
+  a.acts = (uint8_t*)acts;
+  return launch_mlp(MODE_FWD_SAVE, a, true, stream);
+}
+
+extern "C" size_t nerfb_packed_weights_bwd_bytes(void) { return (size_t)kChunkAreaBwd + kParamBytes; }
+
+extern "C" int nerfb_pack_weights_bwd(const float* const* h_params, void* packed_bwd, void* stream) {
+  NERFB_REQUIRE(h_params && packed_bwd, "nerfb_pack_weights_bwd: null argument");
+  for (int i = 0; i < 16; ++i) NERFB_REQUIRE(h_params[i], "nerfb_pack_weights_bwd: pts_linears parameter %d missing", i);
+  NERFB_REQUIRE(h_params[NERFB_P_VIEWS_W] && h_params[NERFB_P_VIEWS_B] && h_params[NERFB_P_FEATURE_W] &&
+                    h_params[NERFB_P_FEATURE_B] && h_params[NERFB_P_ALPHA_W] && h_params[NERFB_P_ALPHA_B] &&
+                    h_params[NERFB_P_RGB_W] && h_params[NERFB_P_RGB_B],
+                "nerfb_pack_weights_bwd: view-dependent head parameters missing (the tensor-core backward "
+                "supports use_viewdirs networks only)");
+  PackArgsT pt{};
+  int n = 0;
+  for (int kc = 0; kc < 2; ++kc) pt.ch[n++] = PackChunkT{h_params[NERFB_P_VIEWS_W], 283, 64 * kc, 0};
+  for (int kc = 0; kc < 4; ++kc) pt.ch[n++] = PackChunkT{h_params[NERFB_P_FEATURE_W], 256, 64 * kc, 0};
+  for (int l = 7; l >= 1; --l)
+    for (int kc = 0; kc < 4; ++kc) pt.ch[n++] = PackChunkT{h_params[2 * l], l == 5 ? 319 : 256, 64 * kc, l == 5 ? 63 : 0};
+  PackArgs pa{};
+  pa.use_viewdirs = 1;
+  pa.out_ch = 4;
+  for (int l = 0; l < 8; ++l) pa.bias[l] = h_params[2 * l + 1];
+  pa.bias[8] = h_params[NERFB_P_FEATURE_B];
+  pa.bias[9] = h_params[NERFB_P_VIEWS_B];
+  pa.src[0] = h_params[NERFB_P_ALPHA_W];
+  pa.src[1] = h_params[NERFB_P_ALPHA_B];
+  pa.src[2] = h_params[NERFB_P_RGB_W];
+  pa.src[3] = h_params[NERFB_P_RGB_B];
+  dim3 grid(2, kNumBwdChunks + 1);
+  pack_weights_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(pt, pa, (uint8_t*)packed_bwd);
+  return check_launch("pack_weights_bwd_kernel");
+}
+
+extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* packed_bwd, const void* acts,
+                                        void* gstore, void* stream) {
+  NERFB_REQUIRE(nrows >= 0 && d_raw && packed_bwd && acts && gstore, "nerfb_mlp_bwd_chain_bf16: bad arguments");
+  if (nrows == 0) return NERFB_OK;
+  MlpArgs a{};
+  a.nrows = nrows; a.S = 1; a.use_viewdirs = 1; a.out_ch = 4;
+  a.packed = (const uint8_t*)packed_bwd;
+  a.param_off = kChunkAreaBwd;
+  a.acts = (uint8_t*)acts;
+  a.gstore = (uint8_t*)gstore;
+  a.d_raw = d_raw;
+  return launch_mlp(MODE_BWD, a, true, stream);
 }

@@ -319,4 +319,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return d;
 }
 
+// per bf16 half: 0xFFFF where the half is non-zero (ReLU mask from a stored post-ReLU activation pair)
+__device__ __forceinline__ uint32_t bf16x2_nonzero_mask(uint32_t h2) {
+  uint32_t d;
+  const uint32_t zero = 0;
+  asm("set.neu.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(h2), "r"(zero));
+  return d;
+}
+
 }  // namespace tc05

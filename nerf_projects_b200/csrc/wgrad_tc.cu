@@ -1,0 +1,379 @@
+// Weight gradients of the NeRF MLP on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the autograd-generated  dW_l = dY_l^T X_l,  db_l = colsum(dY_l)  of every nn.Linear of
+// NeRF (nerf.py:24-55) for loss.backward() (ipynb:1274).  Inputs are the training tile stores
+// written by the fused forward (X_l: layer inputs) and by the data-gradient chain (dY_l), both
+// as bf16 panel images [128 samples x 64 features] in the UMMA 128B-swizzled layout.  Here the
+// contraction runs over SAMPLES, i.e. over the rows of those images, so both operands are read
+// as MN-major tiles straight from the stored layout (no transposes anywhere).
+//
+//   * one CTA per SM (cta_group::1), a classic warp-specialised GEMM: warp 0 streams 64-sample
+//     stages (A = dY panels, B = X panels, 8 KB bulk copies, 3-stage mbarrier ring), warp 1 issues
+//     UMMA M=128 x N=256|64 x K=16 into fp32 TMEM accumulators that hold a layer's whole dW
+//     (2 x 128 x 256 = all 512 columns), warps 2..5 reduce the small things on CUDA cores from
+//     the same staged tiles (bias gradients = column sums of dY; alpha/rgb head gradients =
+//     d_raw-weighted column sums of h7 / hv) and, at the end of a work item, drain TMEM with
+//     red.global.add.f32 into the fp32 gradient tensors;
+//   * work = (layer job, range of stages): the virtual timeline sum_j bytes_j * nstages is cut
+//     into gridDim equal pieces, so the kernel is a split-K GEMM over all jobs at once and every
+//     byte of X / dY is read from HBM exactly once per job that needs it.
+// Bound: HBM (10.4 KB per sample against 1.19 MFLOP), see DESIGN.md.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "mlp_layout.cuh"
+
+namespace nerfb {
+using namespace tc05;
+
+tc05::Watch get_watch();  // umma_selftest.cu
+
+constexpr int kWgThreads = 192;             // warp 0 loader, warp 1 mma, warps 2..5 simt + epilogue
+constexpr int kStageRows = 64;              // samples per stage
+constexpr int kHalfPanel = kPanel / 2;      // 64 rows x 128 B
+constexpr int kMaxStagePanels = 9;
+constexpr int kStageDraw = kMaxStagePanels * kHalfPanel;   // d_raw slice [64][4] fp32
+constexpr int kStageStride = kStageDraw + 1024;            // 74752, multiple of 1024
+constexpr int kWgStages = 3;
+constexpr int kWgSmBars = kWgStages * kStageStride;
+constexpr int kWgSmemBytes = kWgSmBars + 128;
+static_assert(kWgSmemBytes <= 232448, "shared memory budget exceeded");
+static_assert(kStageStride % 1024 == 0, "stage buffers must keep the swizzle phase");
+
+enum { SIMT_NONE = 0, SIMT_ALPHA = 1, SIMT_RGB = 2 };
+
+struct WJob {
+  uint32_t a_off;          // gradient panels inside a bwd tile (gstore)
+  int a_panels;            // 4 (256 outputs: two M halves) or 2 (128 outputs)
+  uint32_t b_off[2];       // activation panel groups inside a fwd tile (acts)
+  int b_panels[2];         // 4, 1 or 0
+  uint32_t x_off;          // extra activation panels staged for the SIMT reduction (hv)
+  int x_panels;
+  float* dW; int ld;       // destination [outputs, ld]
+  int col_off[2], ncols[2];// group g lands at dW[:, col_off[g] : col_off[g]+ncols[g]]
+  float* dbias;            // += colsum(dY) or null
+  int simt;                // SIMT_*
+  float* head_w;           // alpha_linear.weight [1,256] / rgb_linear.weight [3,128] gradient
+  float* head_b;
+  int weight;              // relative cost of one stage (bytes / 1024)
+};
+constexpr int kMaxJobs = 12;
+struct WArgs {
+  WJob jobs[kMaxJobs];
+  int njobs;
+  const uint8_t* acts;
+  const uint8_t* gstore;
+  const float* d_raw;      // [ntiles*128, 4], zero beyond the real rows
+  long long nstages;       // 2 per 128-sample tile
+  Watch watch;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_constant__ WArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  __shared__ uint32_t tmem_slot;
+  auto bar = [&](int i) -> uint32_t { return sbase + kWgSmBars + 8 * i; };
+  const int B_FULL = 0, B_EMPTY = kWgStages, B_ACC = 2 * kWgStages, B_FREE = 2 * kWgStages + 1;
+
+  if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xB11, sbase, 0);
+  if (tid == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(bar(B_FULL + s), 1);
+      mbar_init(bar(B_EMPTY + s), 1 + 4);     // tcgen05.commit + one arrive per SIMT warp
+    }
+    mbar_init(bar(B_ACC), 1);
+    mbar_init(bar(B_FREE), 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(smem_u32(&tmem_slot), 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // ---- my slice of the virtual timeline (units: job weight x stages)
+  long long total = 0;
+  for (int j = 0; j < a.njobs; ++j) total += (long long)a.jobs[j].weight * a.nstages;
+  const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+  // item iterator (identical in every role): job j, stages [s0, s1)
+  auto item = [&](int j, long long& s0, long long& s1) -> bool {
+    long long base = 0;
+    for (int q = 0; q < j; ++q) base += (long long)a.jobs[q].weight * a.nstages;
+    const long long w = a.jobs[j].weight;
+    const long long b0 = lo > base ? lo : base;
+    const long long e0 = hi < base + w * a.nstages ? hi : base + w * a.nstages;
+    if (e0 <= b0) return false;
+    s0 = (b0 - base + w - 1) / w;
+    s1 = (e0 - base + w - 1) / w;
+    return s1 > s0;
+  };
+
+  if (warp == 0) {
+    // ===================== loader
+    if (lane == 0) {
+      long long g = 0;
+      for (int j = 0; j < a.njobs; ++j) {
+        long long s0, s1;
+        if (!item(j, s0, s1)) continue;
+        const WJob& jb = a.jobs[j];
+        const int npan = jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + jb.x_panels;
+        for (long long s = s0; s < s1; ++s, ++g) {
+          const int slot = (int)(g % kWgStages);
+          if (g >= kWgStages) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((g / kWgStages) + 1) & 1), a.watch, 0x1100 + j);
+          const uint32_t dst = sbase + slot * kStageStride;
+          const uint32_t fb = bar(B_FULL + slot);
+          mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u);
+          const size_t tile = (size_t)(s >> 1), half = (size_t)(s & 1) * kHalfPanel;
+          const uint8_t* gt = a.gstore + tile * kBwdTileBytes + jb.a_off + half;
+          const uint8_t* ft = a.acts + tile * kFwdTileBytes + half;
+          int p = 0;
+          for (int i = 0; i < jb.a_panels; ++i, ++p) bulk_g2s(dst + p * kHalfPanel, gt + (size_t)i * kPanel, kHalfPanel, fb);
+          for (int grp = 0; grp < 2; ++grp)
+            for (int i = 0; i < jb.b_panels[grp]; ++i, ++p)
+              bulk_g2s(dst + p * kHalfPanel, ft + jb.b_off[grp] + (size_t)i * kPanel, kHalfPanel, fb);
+          for (int i = 0; i < jb.x_panels; ++i, ++p)
+            bulk_g2s(dst + p * kHalfPanel, ft + jb.x_off + (size_t)i * kPanel, kHalfPanel, fb);
+          bulk_g2s(dst + kStageDraw, a.d_raw + (size_t)s * kStageRows * 4, 1024, fb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues)
+    long long g = 0;
+    int nitem = 0;
+    for (int j = 0; j < a.njobs; ++j) {
+      long long s0, s1;
+      if (!item(j, s0, s1)) continue;
+      const WJob& jb = a.jobs[j];
+      if (nitem > 0) {                       // accumulators of the previous item must have been drained
+        mbar_wait(bar(B_FREE), (uint32_t)((nitem - 1) & 1), a.watch, 0x1200 + j);
+        tc_fence_after();
+      }
+      const int nmh = jb.a_panels / 2;
+      const uint32_t idesc0 = make_idesc_bf16_mn(128, 64 * jb.b_panels[0]);
+      const uint32_t idesc1 = make_idesc_bf16_mn(128, jb.b_panels[1] ? 64 * jb.b_panels[1] : 64);
+      for (long long s = s0; s < s1; ++s, ++g) {
+        const int slot = (int)(g % kWgStages);
+        mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1300 + j);
+        tc_fence_after();
+        const uint32_t st = sbase + slot * kStageStride;
+        if (elect_one()) {
+          for (int mh = 0; mh < nmh; ++mh) {
+            const uint64_t da = make_sdesc_sw128_mn(st + mh * 2 * kHalfPanel, kHalfPanel);
+            const uint64_t db0 = make_sdesc_sw128_mn(st + jb.a_panels * kHalfPanel, kHalfPanel);
+            const uint32_t acc0 = (s > s0) ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < kStageRows / 16; ++k)
+              umma_bf16<1>(tmem_base + mh * 256, da + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc0,
+                           (k > 0) ? 1u : acc0);
+            if (jb.b_panels[1]) {
+              const uint64_t db1 = make_sdesc_sw128_mn(st + (jb.a_panels + jb.b_panels[0]) * kHalfPanel, kHalfPanel);
+              const uint32_t d1 = tmem_base + mh * 256 + 64 * jb.b_panels[0];   // only used with one M half (views)
+#pragma unroll
+              for (int k = 0; k < kStageRows / 16; ++k)
+                umma_bf16<1>(d1, da + (uint64_t)(k * 128), db1 + (uint64_t)(k * 128), idesc1, (k > 0) ? 1u : acc0);
+            }
+          }
+          umma_commit<1>(bar(B_EMPTY + slot));
+          if (s + 1 == s1) umma_commit<1>(bar(B_ACC));
+        }
+        __syncwarp();
+      }
+      ++nitem;
+    }
+  } else {
+    // ===================== SIMT reductions + epilogue (warps 2..5, TMEM lane quarter = warp % 4)
+    const int st_id = tid - 64;                 // 0..127
+    const int q = warp & 3;
+    const int row_in_half = 32 * q + lane;      // accumulator lane = output feature within the M half
+    long long g = 0;
+    int nitem = 0;
+    for (int j = 0; j < a.njobs; ++j) {
+      long long s0, s1;
+      if (!item(j, s0, s1)) continue;
+      const WJob& jb = a.jobs[j];
+      // per-thread SIMT accumulators
+      float bsum0 = 0.f, bsum1 = 0.f;           // bias: columns 2*st_id, 2*st_id+1 of dY
+      float h0[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};   // head weight gradients
+      float hb[4] = {0.f, 0.f, 0.f, 0.f};       // sums of d_raw components (thread 0)
+      const bool do_bias = jb.dbias != nullptr && (st_id >> 5) < jb.a_panels;
+      const int wpan = st_id >> 5, wq = (st_id & 31) >> 2, wb = (st_id & 3) << 2;
+      for (long long s = s0; s < s1; ++s, ++g) {
+        const int slot = (int)(g % kWgStages);
+        mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1400 + j);
+        const uint8_t* stp = smem + slot * kStageStride;
+        const float4* draw = reinterpret_cast<const float4*>(stp + kStageDraw);
+        if (do_bias) {
+          const uint8_t* pa = stp + wpan * kHalfPanel + wb;
+#pragma unroll 8
+          for (int r = 0; r < kStageRows; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(pa + r * 128 + ((wq ^ (r & 7)) << 4));
+            bsum0 += __uint_as_float(w << 16);
+            bsum1 += __uint_as_float(w & 0xFFFF0000u);
+          }
+        }
+        if (jb.simt == SIMT_ALPHA) {
+          // d alpha_linear.weight[c] += sum_r dsigma[r] * h7[r][c]   (h7 = B group 0, 4 panels)
+          const uint8_t* pb = stp + (jb.a_panels + wpan) * kHalfPanel + wb;
+#pragma unroll 8
+          for (int r = 0; r < kStageRows; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(pb + r * 128 + ((wq ^ (r & 7)) << 4));
+            const float ds = draw[r].w;
+            h0[0] = fmaf(ds, __uint_as_float(w << 16), h0[0]);
+            h1[0] = fmaf(ds, __uint_as_float(w & 0xFFFF0000u), h1[0]);
+          }
+          if (st_id == 0)
+            for (int r = 0; r < kStageRows; ++r) hb[3] += draw[r].w;
+        } else if (jb.simt == SIMT_RGB) {
+          // d rgb_linear.weight[k][c] += sum_r d_rgb[r][k] * hv[r][c]   (hv = extra panels, 2 x 64 columns)
+          const int word = st_id & 63, par = st_id >> 6;
+          const uint8_t* px = stp + (jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + (word >> 5)) * kHalfPanel +
+                              ((word & 3) << 2);
+          const int xq = (word & 31) >> 2;
+#pragma unroll 8
+          for (int r = par; r < kStageRows; r += 2) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(px + r * 128 + ((xq ^ (r & 7)) << 4));
+            const float4 d = draw[r];
+            const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xFFFF0000u);
+            h0[0] = fmaf(d.x, x0, h0[0]); h1[0] = fmaf(d.x, x1, h1[0]);
+            h0[1] = fmaf(d.y, x0, h0[1]); h1[1] = fmaf(d.y, x1, h1[1]);
+            h0[2] = fmaf(d.z, x0, h0[2]); h1[2] = fmaf(d.z, x1, h1[2]);
+          }
+          if (st_id == 0)
+            for (int r = 0; r < kStageRows; ++r) { hb[0] += draw[r].x; hb[1] += draw[r].y; hb[2] += draw[r].z; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_EMPTY + slot));
+      }
+      // ---- flush the SIMT sums
+      if (do_bias) {
+        atomicAdd(jb.dbias + 2 * st_id, bsum0);
+        atomicAdd(jb.dbias + 2 * st_id + 1, bsum1);
+      }
+      if (jb.simt == SIMT_ALPHA) {
+        atomicAdd(jb.head_w + 2 * st_id, h0[0]);
+        atomicAdd(jb.head_w + 2 * st_id + 1, h1[0]);
+        if (st_id == 0) atomicAdd(jb.head_b, hb[3]);
+      } else if (jb.simt == SIMT_RGB) {
+        const int word = st_id & 63;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          atomicAdd(jb.head_w + k * 128 + 2 * word, h0[k]);
+          atomicAdd(jb.head_w + k * 128 + 2 * word + 1, h1[k]);
+        }
+        if (st_id == 0)
+          for (int k = 0; k < 3; ++k) atomicAdd(jb.head_b + k, hb[k]);
+      }
+      // ---- drain the accumulators: dW[out, col_off + c] += D[out, c]
+      mbar_wait(bar(B_ACC), (uint32_t)(nitem & 1), a.watch, 0x1500 + j);
+      tc_fence_after();
+      const int nmh = jb.a_panels / 2;
+      for (int mh = 0; mh < nmh; ++mh) {
+        const int out = 128 * mh + row_in_half;
+        int cbase = 0;
+        for (int grp = 0; grp < 2; ++grp) {
+          const int ncol_g = 64 * jb.b_panels[grp];
+          float* dst = jb.dW + (size_t)out * jb.ld + jb.col_off[grp];
+          for (int c0 = 0; c0 < ncol_g; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + mh * 256 + cbase + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < jb.ncols[grp]) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+          }
+          cbase += ncol_g;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_FREE));
+      ++nitem;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace nerfb
+
+using namespace nerfb;
+
+extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore, const float* d_raw_padded,
+                                    float* const* h_grads, void* stream) {
+  NERFB_REQUIRE(nrows >= 0 && acts && gstore && d_raw_padded && h_grads, "nerfb_mlp_wgrad_bf16: bad arguments");
+  for (int i = 0; i < NERFB_P_OUTPUT_W; ++i)
+    NERFB_REQUIRE(h_grads[i], "nerfb_mlp_wgrad_bf16: gradient tensor %d missing", i);
+  if (nrows == 0) return NERFB_OK;
+  WArgs a{};
+  int n = 0;
+  auto G = [&](int i) { return h_grads[i]; };
+  auto plain = [&](uint32_t a_off, uint32_t b_off, float* dW, int ld, int col_off, float* dbias) {
+    WJob j{};
+    j.a_off = a_off; j.a_panels = 4;
+    j.b_off[0] = b_off; j.b_panels[0] = 4;
+    j.dW = dW; j.ld = ld; j.col_off[0] = col_off; j.ncols[0] = 256;
+    j.dbias = dbias;
+    j.weight = 8 * 8 + 1;
+    return j;
+  };
+  auto narrow = [&](uint32_t a_off, float* dW, int ld, float* dbias) {     // gamma(x) block: 63 valid columns
+    WJob j{};
+    j.a_off = a_off; j.a_panels = 4;
+    j.b_off[0] = kFXg; j.b_panels[0] = 1;
+    j.dW = dW; j.ld = ld; j.col_off[0] = 0; j.ncols[0] = 63;
+    j.dbias = dbias;
+    j.weight = 5 * 8 + 1;
+    return j;
+  };
+  const uint32_t dY = kGY, hL = kFH;
+  a.jobs[n++] = narrow(dY + 0 * 4 * kPanel, G(0), 63, G(1));                                          // pts_linears.0
+  for (int l = 1; l <= 7; ++l) {
+    if (l == 5) {
+      a.jobs[n++] = plain(dY + 5 * 4 * kPanel, hL + 4 * 4 * kPanel, G(10), 319, 63, G(11));           // [. | h4] part
+      a.jobs[n++] = narrow(dY + 5 * 4 * kPanel, G(10), 319, nullptr);                                 // gamma(x) part
+    } else {
+      a.jobs[n++] = plain(dY + l * 4 * kPanel, hL + (l - 1) * 4 * kPanel, G(2 * l), 256, 0, G(2 * l + 1));
+    }
+  }
+  {  // feature_linear (+ alpha_linear on CUDA cores from the same h7 tiles)
+    WJob j = plain(kGFeat, hL + 7 * 4 * kPanel, G(NERFB_P_FEATURE_W), 256, 0, G(NERFB_P_FEATURE_B));
+    j.simt = SIMT_ALPHA;
+    j.head_w = G(NERFB_P_ALPHA_W); j.head_b = G(NERFB_P_ALPHA_B);
+    a.jobs[n++] = j;
+  }
+  {  // views_linears.0: dhv^T [feature | gamma(d)]  (+ rgb_linear on CUDA cores from hv)
+    WJob j{};
+    j.a_off = kGHv; j.a_panels = 2;
+    j.b_off[0] = kFFeat; j.b_panels[0] = 4; j.col_off[0] = 0; j.ncols[0] = 256;
+    j.b_off[1] = kFDg; j.b_panels[1] = 1; j.col_off[1] = 256; j.ncols[1] = 27;
+    j.x_off = kFHv; j.x_panels = 2;
+    j.dW = G(NERFB_P_VIEWS_W); j.ld = 283;
+    j.dbias = G(NERFB_P_VIEWS_B);
+    j.simt = SIMT_RGB;
+    j.head_w = G(NERFB_P_RGB_W); j.head_b = G(NERFB_P_RGB_B);
+    j.weight = 9 * 8 + 1;
+    a.jobs[n++] = j;
+  }
+  a.njobs = n;
+  a.acts = (const uint8_t*)acts;
+  a.gstore = (const uint8_t*)gstore;
+  a.d_raw = d_raw_padded;
+  a.nstages = 8 * ((nrows + kSuperRows - 1) / kSuperRows);    // 4 tiles x 2 stages per 512-row super-tile
+  a.watch = get_watch();
+  static bool attr_set = false;
+  if (!attr_set) {
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr_set = true;
+  }
+  int grid = sm_count();
+  const long long units = (long long)a.njobs * a.nstages;
+  if (units < grid) grid = (int)units;
+  nerf_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, as_stream(stream)>>>(a);
+  return check_launch("nerf_wgrad_kernel");
+}

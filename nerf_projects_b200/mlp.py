@@ -221,6 +221,84 @@ def forward(net, R, S, rays, z, pts=None, viewdirs=None):
     return forward_fp32(net, R, S, rays, z, pts, viewdirs)
 
 
+# ------------------------------------------------- bf16 backward (tensor cores)
+
+TRAIN_ROWS_PER_CHUNK = 1 << 18     # samples per backward chunk: 2.6 GB + 2.5 GB of tile stores
+_workspaces = {}
+
+
+def packed_weights_bwd(net) -> torch.Tensor:
+    """Transposed bf16 weight images for the data-gradient chain (repacked when a parameter changed)."""
+    params = dict(net.named_parameters())
+    key = tuple((p.data_ptr(), p._version) for p in params.values())
+    cached = getattr(net, "_packed_bwd", None)
+    if cached is not None and getattr(net, "_packed_bwd_key", None) == key:
+        return cached
+    dev = net.pts_linears[0].weight.device
+    nbytes = ops.packed_weights_bwd_bytes()
+    if cached is None or cached.numel() != nbytes or cached.device != dev:
+        cached = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ops.pack_weights_bwd(_param_ptrs(params), cached)
+    net._packed_bwd, net._packed_bwd_key = cached, key
+    return cached
+
+
+def _param_ptrs(named):
+    ptrs = [None] * L.NERFB_NUM_PARAMS
+    for name, p in named.items():
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            raise L.NerfB200Error(f"tensor {name} must be contiguous fp32")
+        ptrs[_P_INDEX[name]] = p.data_ptr()
+    return ptrs
+
+
+def _train_workspace(dev, nrows):
+    """(acts, gstore) tile stores for up to nrows samples, cached per device (grown on demand)."""
+    need = (ops.train_store_bytes(nrows, 0), ops.train_store_bytes(nrows, 1))
+    ws = _workspaces.get(dev)
+    if ws is None or ws[0].numel() < need[0] or ws[1].numel() < need[1]:
+        ws = None
+        _workspaces.pop(dev, None)
+        ws = (torch.empty(need[0], dtype=torch.uint8, device=dev), torch.empty(need[1], dtype=torch.uint8, device=dev))
+        _workspaces[dev] = ws
+    return ws
+
+
+def supports_bf16_backward(net) -> bool:
+    return bool(net.is_canonical() and net.use_viewdirs)
+
+
+def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.Tensor]:
+    """Parameter gradients of sum(raw * d_raw) on the tensor cores: per ray chunk the fused forward
+    is re-run with its layer inputs stored (recompute), then the data-gradient chain, then the
+    weight-gradient GEMMs.  Nothing is kept between forward and backward except rays, z and d_raw."""
+    if not supports_bf16_backward(net):
+        raise L.NerfB200Error("the tensor-core backward supports the canonical use_viewdirs network only")
+    dev = net.pts_linears[0].weight.device
+    named = dict(net.named_parameters())
+    grads = {n: torch.zeros_like(p) for n, p in named.items()}
+    gptrs = _param_ptrs(grads)
+    packed, packed_bwd = packed_weights(net), packed_weights_bwd(net)
+    step = max(1, TRAIN_ROWS_PER_CHUNK // S)
+    acts, gstore = _train_workspace(dev, min(R, step) * S)
+    d_raw = L.f32c(d_raw).view(-1, 4)
+    for r0 in range(0, R, step):
+        r1 = min(R, r0 + step)
+        n = (r1 - r0) * S
+        npad = (n + 511) // 512 * 512
+        d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
+        d_pad[:n].copy_(d_raw[r0 * S:r1 * S])
+        raw_tmp = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        ops.mlp_fwd_save_bf16(r1 - r0, S, _slice_rows(rays, r0, r1), _slice_rows(z, r0, r1),
+                              _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), packed, raw_tmp, acts)
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore)
+        ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs)
+    return grads
+
+
 def backward(net, R, S, rays, z, pts, viewdirs, d_raw):
-    # gradients are computed by the fp32 kernels in both modes (round 1)
+    """bf16 mode: tensor-core backward for the canonical view-dependent network, fp32 CUDA-core kernels
+    otherwise (other architectures, validation mode)."""
+    if _PRECISION == "bf16" and supports_bf16_backward(net):
+        return backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw)
     return backward_fp32(net, R, S, rays, z, pts, viewdirs, d_raw)

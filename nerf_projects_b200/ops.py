@@ -256,6 +256,43 @@ def _mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, ra
     return raw
 
 
+# ------------------------------------------ tensor-core MLP backward (bf16)
+
+def train_store_bytes(nrows: int, which: int) -> int:
+    return int(L.load().nerfb_train_store_bytes(int(nrows), int(which)))
+
+
+def packed_weights_bwd_bytes() -> int:
+    return int(L.load().nerfb_packed_weights_bwd_bytes())
+
+
+def pack_weights_bwd(param_ptrs: Sequence[Optional[int]], packed_bwd: torch.Tensor):
+    arr = (C.c_void_p * L.NERFB_NUM_PARAMS)(*[p if p else None for p in param_ptrs])
+    L.check(L.load().nerfb_pack_weights_bwd(arr, L.ptr(packed_bwd), L.stream()), "nerfb_pack_weights_bwd")
+    _count()
+
+
+def mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed, raw, acts):
+    L.check(L.load().nerfb_mlp_fwd_save_bf16(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
+                                             L.ptr(z), L.ptr(pts), L.ptr(viewdirs), L.ptr(packed), L.ptr(raw),
+                                             L.ptr(acts), L.stream()), "nerfb_mlp_fwd_save_bf16")
+    _count()
+    return raw
+
+
+def mlp_bwd_chain_bf16(nrows, d_raw, packed_bwd, acts, gstore):
+    L.check(L.load().nerfb_mlp_bwd_chain_bf16(int(nrows), L.ptr(d_raw), L.ptr(packed_bwd), L.ptr(acts),
+                                              L.ptr(gstore), L.stream()), "nerfb_mlp_bwd_chain_bf16")
+    _count()
+
+
+def mlp_wgrad_bf16(nrows, acts, gstore, d_raw_padded, grad_ptrs: Sequence[Optional[int]]):
+    arr = (C.c_void_p * L.NERFB_NUM_PARAMS)(*[p if p else None for p in grad_ptrs])
+    L.check(L.load().nerfb_mlp_wgrad_bf16(int(nrows), L.ptr(acts), L.ptr(gstore), L.ptr(d_raw_padded), arr,
+                                          L.stream()), "nerfb_mlp_wgrad_bf16")
+    _count()
+
+
 def umma_selftest(A, B, cta_group=1):
     N, K = B.shape
     assert A.shape == (128 * cta_group, K)
