@@ -240,6 +240,43 @@ def test_train_step_gradients_vs_reference_golden():
     assert any(not torch.equal(a, b) for a, b in zip(before, grad_vars))
 
 
+def test_train_step_gradients_bf16_tensor_core_backward_vs_reference_golden():
+    """The same training step in bf16 mode: forward AND backward on the tensor cores (forward-with-save,
+    data-gradient chain, weight-gradient kernel).  bf16 rounding of the forward flips the ReLU mask of
+    near-zero units, so gradients are compared by direction and norm (fp32 validation mode above is the
+    strict statement; tests/test_gpu_tc.py checks the backward kernels teacher-forced to 1e-6)."""
+    import nerf_projects_b200 as nb
+    from nerf_projects_b200 import mlp
+    g = gold("train_grads")
+    assert nb.get_precision() == "bf16"
+    kw, kw_train, grad_vars, optim = build("render_c1_sharp")
+    assert mlp.supports_bf16_backward(kw["network_fn"])
+    K1, _ = O.blender_camera(800, 800, 30.0)
+    rgb, disp, acc, extras = nb.render(800, 800, K1, chunk=32768, rays=(T(g["rays_o"]).to(DEV), T(g["rays_d"]).to(DEV)),
+                                       near=2., far=6., retraw=True, **kw)
+    target = T(g["target"]).to(DEV)
+    loss = nb.img2mse(rgb, target) + nb.img2mse(extras["rgb0"], target)
+    optim.zero_grad()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-2
+    worst = 1.0
+    for tag, net in (("c", kw["network_fn"]), ("f", kw["network_fine"])):
+        for name, prm in net.named_parameters():
+            key = f"{tag}.{name}"
+            n = float(g[key + ".norm"])
+            got = npy(prm.grad).astype(np.float64)
+            assert abs(np.linalg.norm(got) - n) <= 0.2 * max(n, 1e-7), (key, np.linalg.norm(got), n)
+            if key + ".full" in g:
+                ref = g[key + ".full"].astype(np.float64)
+                cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+                worst = min(worst, cos)
+                assert cos > 0.95, (key, cos)
+    print(f"bf16 tensor-core backward vs reference gradients: worst cosine {worst:.4f}")
+    before = [p.detach().clone() for p in grad_vars]
+    optim.step()
+    assert any(not torch.equal(a, b) for a, b in zip(before, grad_vars))
+
+
 def test_train_step_with_perturb_and_noise_runs_and_is_finite():
     import nerf_projects_b200 as nb
     nb.set_precision("fp32")

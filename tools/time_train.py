@@ -1,0 +1,57 @@
+"""Per-kernel CUDA-event timing of one training step's MLP backward (GPU box only).
+
+    python tools/time_train.py [rays] [reps]
+Prints ms and achieved TFLOP/s / GB/s of: fused forward, forward-with-save, data-gradient chain,
+weight-gradient kernel on a [rays x 192] fine-network batch."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nerf_projects_b200 as nb  # noqa: E402
+from nerf_projects_b200 import mlp, ops  # noqa: E402
+from oracle import nerf_oracle as O  # noqa: E402  (seeded parameters only)
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+S = 192
+dev = "cuda"
+net = nb.NeRF(8, 256, 63, 27, 5, [4], True).to(dev)
+net.load_state_dict(O.to_torch(O.make_params(1, use_viewdirs=True, output_ch=5)))
+gen = torch.Generator().manual_seed(0)
+rays = torch.cat([torch.randn(R, 3, generator=gen), torch.randn(R, 3, generator=gen), torch.full((R, 1), 2.0),
+                  torch.full((R, 1), 6.0), torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=-1)],
+                 -1).to(dev)
+z = (torch.rand(R, S, generator=gen) * 4 + 2).sort(-1)[0].to(dev)
+n = R * S
+npad = (n + 511) // 512 * 512
+d_pad = torch.zeros(npad, 4, device=dev)
+d_pad[:n] = torch.randn(n, 4, generator=gen).to(dev)
+packed, packed_bwd = mlp.packed_weights(net), mlp.packed_weights_bwd(net)
+acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device=dev)
+gstore = torch.empty(ops.train_store_bytes(n, 1), dtype=torch.uint8, device=dev)
+raw = torch.empty(n, 4, device=dev)
+grads = {k: torch.zeros_like(p) for k, p in net.named_parameters()}
+gptrs = mlp._param_ptrs(grads)
+
+legs = {
+    "fwd": (lambda: ops._mlp_fwd_bf16(R, S, rays, z, None, None, True, 5, packed, raw), 1186816, 20),
+    "fwd_save": (lambda: ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts), 1186816, 5 * 1024 + 20),
+    "bwd_chain": (lambda: ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore), 2 * 557696,
+                  (4 * 8 + 2) * 128 + 38 * 128 + 16),
+    "wgrad": (lambda: ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs), 1186816, 10.4 * 1024),
+}
+for name, (fn, flop, bytes_per_row) in legs.items():
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:10s} {ms:8.3f} ms   {n * flop / ms / 1e9:8.1f} TFLOP/s   {n * bytes_per_row / ms / 1e6:8.1f} GB/s "
+          f"(algorithmic)   rows={n}")
