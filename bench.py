@@ -273,7 +273,7 @@ def main():
         tr_ms = timed(step_train, tr_steps)
         train = {"value": n_batch * tr_steps / (tr_ms * 1e-3), "unit": "rays/s", "ms_per_step": tr_ms / tr_steps,
                  "config": f"{n_batch}-ray batch, 64+128, perturb=1, raw_noise_std=1, MSE(rgb)+MSE(rgb0), Adam; "
-                           "forward bf16 tensor cores, backward fp32 CUDA-core kernels with recompute"}
+                           "forward + backward on bf16 tensor cores (recompute-with-save, data-gradient chain, split-K weight gradients)"}
 
     rays_per_step = n_rays * world
     value = rays_per_step * args.steps / (total_ms * 1e-3)

@@ -208,6 +208,9 @@ int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float
 /* Same for MN-major operands (the wgrad form): C[128,N] = At^T Bt, At [K,128], Bt [K,N] row-major,
  * K multiple of 16 (<= 128), N multiple of 64 (<= 256), single CTA. */
 int nerfb_umma_selftest_mn(int N, int K, const float* At, const float* Bt, float* C, void* stream);
+/* Probe (tools/probe_bulk.py): cycles per chunk of the 1-D bulk-copy path, per CTA, ring of `depth`. */
+int nerfb_bulk_probe(const void* src, int src_bytes, int nchunks, int chunk_bytes, int pieces, int depth,
+                     int nblocks, long long* out_cycles, void* stream);
 /* Debug: when dev_buf != NULL, block 0 of the fused MLP kernel records a clock64 timeline
  * (3 regions x 4096 entries: loader, MMA issuer, epilogue; entry = tag<<44 | cycles).
  * Pass NULL to switch tracing off. */

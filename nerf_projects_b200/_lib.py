@@ -11,7 +11,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
+# NERFB_VARIANT selects an experiment build (tools/, never set in production); the default is the product library
+_VARIANT = os.environ.get("NERFB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libnerf_b200_{_VARIANT}.so" if _VARIANT else "libnerf_b200.so")
 
 NERFB_NO_VIEWS = -1000
 NERFB_NUM_PARAMS = 26
@@ -47,6 +49,7 @@ _SIGS = {
     "nerfb_mlp_wgrad_bf16": ([_ll, _vp, _vp, _vp, C.POINTER(_vp), _vp], _i),
     "nerfb_umma_selftest": ([_i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_umma_selftest_mn": ([_i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_bulk_probe": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "nerfb_watchdog_record": ([], C.POINTER(C.c_ulonglong)),
     "nerfb_set_trace": ([_vp], _i),
     "nerfb_adam_step": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll),

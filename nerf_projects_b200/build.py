@@ -11,14 +11,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libnerf_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# experiments: NERFB_VARIANT=name NERFB_DEFINES="-DX=1" builds libnerf_b200_<name>.so beside the product library
+VARIANT = os.environ.get("NERFB_VARIANT", "")
+LIB = os.path.join(HERE, f"libnerf_b200_{VARIANT}.so" if VARIANT else "libnerf_b200.so")
+OBJ_DIR = os.path.join(HERE, "build", VARIANT) if VARIANT else os.path.join(HERE, "build")
 
 SOURCES = ["api.cu", "rays.cu", "embed.cu", "linear_fp32.cu", "composite.cu", "sample_pdf.cu", "adam.cu",
            "umma_selftest.cu", "mlp_tc.cu", "wgrad_tc.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NERFB_DEFINES", "").split()
 
 
 def _nvcc() -> str:

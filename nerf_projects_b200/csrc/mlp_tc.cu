@@ -23,6 +23,7 @@
 //     accumulators, the rgb head in fp32 from the fp32 view
 //     layer activations;
 //   * every barrier wait is bounded by a watchdog (tc05.cuh).
+#include <cstdlib>
 #include "common.cuh"
 #include "tc05.cuh"
 #include "mlp_layout.cuh"
@@ -471,11 +472,18 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             float sig = 0.f;
             // software pipeline: the TMEM load of batch b+1 is in flight while batch b is processed
             uint32_t v[2][32];
+#ifndef NERFB_EXP_NOTMEM
             tmem_ld32(taddr + 128 * hh, v[0]);
+#else
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[0][i] = row * 77 + i; v[1][i] = row * 31 + i; }
+#endif
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
+#ifndef NERFB_EXP_NOTMEM
               tmem_ld_wait();
               if (b < 3) tmem_ld32(taddr + 128 * hh + 32 * (b + 1), v[(b + 1) & 1]);
+#endif
               const uint32_t (&vv)[32] = v[b & 1];
               float x[32];
 #pragma unroll
@@ -503,7 +511,11 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
               }
               const int col0 = 128 * hh + 32 * b;
+#ifndef NERFB_EXP_NOSTS
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+#else
+              if (w[0] == 0x12345678u) store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+#endif
             }
             if (l == 7) s_sig[(t * 2 + hh) * 128 + row] = sig;
           } else if (l == 7) {
@@ -600,6 +612,15 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           gtile[t] = a.gstore + T * kBwdTileBytes;
         }
         float dsig[2];
+        if (et == 0) {
+          bulk_prefetch_l2(ftile[0] + kFH + 7 * 4 * kPanel, 4 * kPanel);
+          bulk_prefetch_l2(ftile[1] + kFH + 7 * 4 * kPanel, 4 * kPanel);
+          if (it + 1 < niter) {      // hv tiles of the next super-tile of this cluster
+            const size_t Tn = (size_t)((st + a.nclusters) * 4 + rank);
+            bulk_prefetch_l2(a.acts + Tn * kFwdTileBytes + kFHv, 2 * kPanel);
+            bulk_prefetch_l2(a.acts + (Tn + 2) * kFwdTileBytes + kFHv, 2 * kPanel);
+          }
+        }
         for (int t = 0; t < 2; ++t) {
           // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
           float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -639,6 +660,8 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 dst[i] = __ldg(reinterpret_cast<const uint4*>(pp + sw128_offset(row, ((col0 & 63) >> 3) + i)));
             };
             if (j > 0) { load_mask(0, hm[0]); load_mask(1, hm[1]); }
+            // pull the NEXT layer's mask tile (64 KB) of this tile into L2 a whole layer ahead
+            if (et == 0 && j + 1 < sc.nlayers) bulk_prefetch_l2(ftile[t] + kFH + (m - 1) * 4 * kPanel, 4 * kPanel);
             mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
             done_cnt[t]++;
             if (et == 0) tr(2, 0x700 + j * 2 + t);
@@ -862,6 +885,10 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   }
   a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
   a.nclusters = sm_count() / 2;
+  if (const char* e = getenv("NERFB_MAX_CLUSTERS")) {      // experiments only (contention studies)
+    const int m = atoi(e);
+    if (m > 0 && m < a.nclusters) a.nclusters = m;
+  }
   if (a.nclusters > a.nst) a.nclusters = a.nst;
   a.watch = get_watch();
   a.trace = g_trace;

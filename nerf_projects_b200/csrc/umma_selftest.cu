@@ -168,6 +168,41 @@ umma_selftest_mn_kernel(int N, int K, const float* __restrict__ At, const float*
   if (warp == 0) tmem_dealloc<1>(tmem_base, ncols);
 }
 
+
+// Probe of the 1-D bulk-copy path (global/L2 -> shared): every CTA streams `nchunks` chunks of
+// `chunk_bytes` (split in `pieces` copies) from the same buffer through a ring of `depth` slots and
+// reports cycles per chunk in steady state.  Used to size the weight ring of the fused MLP kernel.
+__global__ void __launch_bounds__(32, 1)
+bulk_probe_kernel(const uint8_t* __restrict__ src, int src_bytes, int nchunks, int chunk_bytes, int pieces, int depth,
+                  long long* __restrict__ out, Watch watch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < depth; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const uint32_t base = smem_u32(smem_raw);
+    const int piece = chunk_bytes / pieces;
+    long long t0 = 0;
+    const int warm = depth * 4;
+    for (int i = 0; i < nchunks + depth; ++i) {
+      const int slot = i % depth;
+      if (i >= depth) mbar_wait(smem_u32(&bars[slot]), (uint32_t)(((i / depth) - 1) & 1), watch, 0x77);
+      if (i == warm) t0 = clock64();
+      if (i < nchunks) {
+        const size_t off = ((size_t)i * chunk_bytes + (size_t)blockIdx.x * 4096) % (size_t)(src_bytes - chunk_bytes);
+        mbar_arrive_expect_tx(smem_u32(&bars[slot]), chunk_bytes);
+        for (int pc = 0; pc < pieces; ++pc)
+          bulk_g2s(base + slot * chunk_bytes + pc * piece, src + (off & ~(size_t)15) + pc * piece, piece,
+                   smem_u32(&bars[slot]));
+      }
+    }
+    out[blockIdx.x] = (clock64() - t0) / (nchunks + depth - warm);
+  }
+}
+
 }  // namespace nerfb
 
 using namespace nerfb;
@@ -214,4 +249,17 @@ extern "C" int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, 
     NERFB_CUDA(cudaLaunchKernelEx(&cfg, umma_selftest_kernel<2>, N, K, A, B, C, w));
   }
   return check_launch("umma_selftest_kernel");
+}
+
+extern "C" int nerfb_bulk_probe(const void* src, int src_bytes, int nchunks, int chunk_bytes, int pieces, int depth,
+                                int nblocks, long long* out_cycles, void* stream) {
+  NERFB_REQUIRE(src && out_cycles && depth >= 1 && depth <= 16 && chunk_bytes % (16 * pieces) == 0 &&
+                    depth * chunk_bytes <= 200 * 1024 && src_bytes > 2 * chunk_bytes && nchunks > 8 * depth,
+                "nerfb_bulk_probe: bad arguments");
+  const size_t smem = (size_t)depth * chunk_bytes + 1024;
+  tc05::Watch w = get_watch();
+  NERFB_CUDA(cudaFuncSetAttribute(bulk_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bulk_probe_kernel<<<nblocks, 32, smem, as_stream(stream)>>>((const uint8_t*)src, src_bytes, nchunks, chunk_bytes,
+                                                             pieces, depth, out_cycles, w);
+  return check_launch("bulk_probe_kernel");
 }

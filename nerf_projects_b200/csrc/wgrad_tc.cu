@@ -195,52 +195,61 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
       long long s0, s1;
       if (!item(j, s0, s1)) continue;
       const WJob& jb = a.jobs[j];
-      // per-thread SIMT accumulators
-      float bsum0 = 0.f, bsum1 = 0.f;           // bias: columns 2*st_id, 2*st_id+1 of dY
-      float h0[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};   // head weight gradients
-      float hb[4] = {0.f, 0.f, 0.f, 0.f};       // sums of d_raw components (thread 0)
-      const bool do_bias = jb.dbias != nullptr && (st_id >> 5) < jb.a_panels;
-      const int wpan = st_id >> 5, wq = (st_id & 31) >> 2, wb = (st_id & 3) << 2;
+      // per-thread SIMT accumulators.  Mapping for 4-panel operands: 16-byte unit u = st_id & 7 (8 columns)
+      // of panel (st_id >> 3) & 3, rows r = (st_id >> 5) mod 4; a warp reads 4 full 128-byte rows per LDS.128.
+      float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias: 8 columns of dY
+      float hs[3][8];                                              // head weight gradients
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hs[k][i] = 0.f;
+      float hb[4] = {0.f, 0.f, 0.f, 0.f};                          // sums of d_raw components (thread 0)
+      const int su = st_id & 7;
+      // dY has 4 panels (rows r = rg4 mod 4) or 2 panels (rows r = rg8 mod 8)
+      const int bpan = jb.a_panels == 4 ? (st_id >> 3) & 3 : (st_id >> 3) & 1;
+      const int brow0 = jb.a_panels == 4 ? (st_id >> 5) : (st_id >> 4);
+      const int bstep = jb.a_panels == 4 ? 4 : 8;
+      const bool do_bias = jb.dbias != nullptr;
+      auto acc8 = [](float (&acc)[8], const uint4 v, const float w) {
+        acc[0] = fmaf(w, __uint_as_float(v.x << 16), acc[0]); acc[1] = fmaf(w, __uint_as_float(v.x & 0xFFFF0000u), acc[1]);
+        acc[2] = fmaf(w, __uint_as_float(v.y << 16), acc[2]); acc[3] = fmaf(w, __uint_as_float(v.y & 0xFFFF0000u), acc[3]);
+        acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]); acc[5] = fmaf(w, __uint_as_float(v.z & 0xFFFF0000u), acc[5]);
+        acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]); acc[7] = fmaf(w, __uint_as_float(v.w & 0xFFFF0000u), acc[7]);
+      };
       for (long long s = s0; s < s1; ++s, ++g) {
         const int slot = (int)(g % kWgStages);
         mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1400 + j);
         const uint8_t* stp = smem + slot * kStageStride;
         const float4* draw = reinterpret_cast<const float4*>(stp + kStageDraw);
         if (do_bias) {
-          const uint8_t* pa = stp + wpan * kHalfPanel + wb;
-#pragma unroll 8
-          for (int r = 0; r < kStageRows; ++r) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(pa + r * 128 + ((wq ^ (r & 7)) << 4));
-            bsum0 += __uint_as_float(w << 16);
-            bsum1 += __uint_as_float(w & 0xFFFF0000u);
+          const uint8_t* pa = stp + bpan * kHalfPanel;
+#pragma unroll 4
+          for (int r = brow0; r < kStageRows; r += bstep) {
+            const uint4 v = *reinterpret_cast<const uint4*>(pa + r * 128 + ((su ^ (r & 7)) << 4));
+            bs[0] += __uint_as_float(v.x << 16); bs[1] += __uint_as_float(v.x & 0xFFFF0000u);
+            bs[2] += __uint_as_float(v.y << 16); bs[3] += __uint_as_float(v.y & 0xFFFF0000u);
+            bs[4] += __uint_as_float(v.z << 16); bs[5] += __uint_as_float(v.z & 0xFFFF0000u);
+            bs[6] += __uint_as_float(v.w << 16); bs[7] += __uint_as_float(v.w & 0xFFFF0000u);
           }
         }
         if (jb.simt == SIMT_ALPHA) {
           // d alpha_linear.weight[c] += sum_r dsigma[r] * h7[r][c]   (h7 = B group 0, 4 panels)
-          const uint8_t* pb = stp + (jb.a_panels + wpan) * kHalfPanel + wb;
-#pragma unroll 8
-          for (int r = 0; r < kStageRows; ++r) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(pb + r * 128 + ((wq ^ (r & 7)) << 4));
-            const float ds = draw[r].w;
-            h0[0] = fmaf(ds, __uint_as_float(w << 16), h0[0]);
-            h1[0] = fmaf(ds, __uint_as_float(w & 0xFFFF0000u), h1[0]);
+          const uint8_t* pb = stp + (jb.a_panels + ((st_id >> 3) & 3)) * kHalfPanel;
+#pragma unroll 4
+          for (int r = st_id >> 5; r < kStageRows; r += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(pb + r * 128 + ((su ^ (r & 7)) << 4));
+            acc8(hs[0], v, draw[r].w);
           }
           if (st_id == 0)
             for (int r = 0; r < kStageRows; ++r) hb[3] += draw[r].w;
         } else if (jb.simt == SIMT_RGB) {
           // d rgb_linear.weight[k][c] += sum_r d_rgb[r][k] * hv[r][c]   (hv = extra panels, 2 x 64 columns)
-          const int word = st_id & 63, par = st_id >> 6;
-          const uint8_t* px = stp + (jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + (word >> 5)) * kHalfPanel +
-                              ((word & 3) << 2);
-          const int xq = (word & 31) >> 2;
-#pragma unroll 8
-          for (int r = par; r < kStageRows; r += 2) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(px + r * 128 + ((xq ^ (r & 7)) << 4));
+          const uint8_t* px = stp + (jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + ((st_id >> 3) & 1)) * kHalfPanel;
+#pragma unroll 2
+          for (int r = st_id >> 4; r < kStageRows; r += 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(px + r * 128 + ((su ^ (r & 7)) << 4));
             const float4 d = draw[r];
-            const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xFFFF0000u);
-            h0[0] = fmaf(d.x, x0, h0[0]); h1[0] = fmaf(d.x, x1, h1[0]);
-            h0[1] = fmaf(d.y, x0, h0[1]); h1[1] = fmaf(d.y, x1, h1[1]);
-            h0[2] = fmaf(d.z, x0, h0[2]); h1[2] = fmaf(d.z, x1, h1[2]);
+            acc8(hs[0], v, d.x); acc8(hs[1], v, d.y); acc8(hs[2], v, d.z);
           }
           if (st_id == 0)
             for (int r = 0; r < kStageRows; ++r) { hb[0] += draw[r].x; hb[1] += draw[r].y; hb[2] += draw[r].z; }
@@ -248,22 +257,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_EMPTY + slot));
       }
-      // ---- flush the SIMT sums
+      // ---- flush the SIMT sums (several row groups add into the same columns)
       if (do_bias) {
-        atomicAdd(jb.dbias + 2 * st_id, bsum0);
-        atomicAdd(jb.dbias + 2 * st_id + 1, bsum1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(jb.dbias + 64 * bpan + 8 * su + i, bs[i]);
       }
       if (jb.simt == SIMT_ALPHA) {
-        atomicAdd(jb.head_w + 2 * st_id, h0[0]);
-        atomicAdd(jb.head_w + 2 * st_id + 1, h1[0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(jb.head_w + 64 * ((st_id >> 3) & 3) + 8 * su + i, hs[0][i]);
         if (st_id == 0) atomicAdd(jb.head_b, hb[3]);
       } else if (jb.simt == SIMT_RGB) {
-        const int word = st_id & 63;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          atomicAdd(jb.head_w + k * 128 + 2 * word, h0[k]);
-          atomicAdd(jb.head_w + k * 128 + 2 * word + 1, h1[k]);
-        }
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(jb.head_w + k * 128 + 64 * ((st_id >> 3) & 1) + 8 * su + i, hs[k][i]);
         if (st_id == 0)
           for (int k = 0; k < 3; ++k) atomicAdd(jb.head_b + k, hb[k]);
       }

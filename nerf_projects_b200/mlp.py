@@ -223,7 +223,7 @@ def forward(net, R, S, rays, z, pts=None, viewdirs=None):
 
 # ------------------------------------------------- bf16 backward (tensor cores)
 
-TRAIN_ROWS_PER_CHUNK = 1 << 18     # samples per backward chunk: 2.6 GB + 2.5 GB of tile stores
+TRAIN_ROWS_PER_CHUNK = 1 << 20     # samples per backward chunk: 5.2 GB + 5.0 GB of tile stores
 _workspaces = {}
 
 
@@ -279,7 +279,8 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
     grads = {n: torch.zeros_like(p) for n, p in named.items()}
     gptrs = _param_ptrs(grads)
     packed, packed_bwd = packed_weights(net), packed_weights_bwd(net)
-    step = max(1, TRAIN_ROWS_PER_CHUNK // S)
+    nchunk = max(1, -(-(R * S) // TRAIN_ROWS_PER_CHUNK))       # even split: no tiny tail chunk
+    step = -(-R // nchunk)
     acts, gstore = _train_workspace(dev, min(R, step) * S)
     d_raw = L.f32c(d_raw).view(-1, 4)
     for r0 in range(0, R, step):
