@@ -60,11 +60,21 @@ class Raw2OutputsFn(Function):
         return d_raw, None, None, None, None
 
 
+def _backward_coarse(ctx, net_c, R, S, rays, z_c, g_raw_c):
+    if ctx.acts_c is not None:
+        grads = mlp.backward_from_saved(net_c, R * S, ctx.acts_c, g_raw_c)
+        ctx.acts_c = None
+        return grads
+    return mlp.backward(net_c, R, S, rays, z_c, None, None, g_raw_c.view(R * S, -1))
+
+
 class RenderRaysFn(Function):
     """The fused render_rays (ipynb:359-492): coarse pass, compositing,
     hierarchical sampling, fine pass, compositing -- differentiable w.r.t. the
-    parameters of both networks.  Forward stores only rays, depths and the
-    4-channel raw outputs; backward recomputes MLP activations chunk by chunk.
+    parameters of both networks.  Forward stores rays, depths, the 4-channel raw
+    outputs and -- bf16 mode, when they fit mlp.SAVE_BUDGET_BYTES -- the bf16 layer
+    inputs of each pass for the tensor-core backward; otherwise the backward
+    recomputes the MLP activations chunk by chunk.
 
     apply(cfg, rays, t_rand, u, noise_c, noise_f, n_coarse_params, *params)
     returns (rgb, disp, acc, depth, weights, raw, z_vals,
@@ -79,7 +89,16 @@ class RenderRaysFn(Function):
         white = cfg["white_bkgd"]
         rays_d = rays[:, 3:6]
         z_c = ops.coarse_z(rays, S, cfg["lindisp"], t_rand)
-        raw_c = mlp.forward(net_c, R, S, rays, z_c).view(R, S, -1)
+        # training: keep the layer inputs of each pass for the backward when they fit (else recompute there)
+        n_cp = len(list(net_c.parameters()))
+        train_c = any(ctx.needs_input_grad[6:6 + n_cp])
+        train_f = any(ctx.needs_input_grad[6 + (n_cp if net_f is not None else 0):])
+        ctx.acts_c = ctx.acts_f = None
+        if train_c and mlp.can_save_forward(net_c, R * S):
+            raw_c, ctx.acts_c = mlp.forward_save_bf16(net_c, R, S, rays, z_c)
+            raw_c = raw_c.view(R, S, -1)
+        else:
+            raw_c = mlp.forward(net_c, R, S, rays, z_c).view(R, S, -1)
         need_w = N_imp > 0
         rgb, disp, acc, weights, depth = ops.raw2outputs_fwd(raw_c, z_c, rays_d, noise_c, white, want_weights=True)
         ctx.cfg = cfg
@@ -89,7 +108,11 @@ class RenderRaysFn(Function):
             det = (t_rand is None and u is None)
             z_f, z_samples, z_std, _ = ops.hierarchical_z(z_c, weights, N_imp, det, u)
             run = net_f if net_f is not None else net_c
-            raw_f = mlp.forward(run, R, S + N_imp, rays, z_f).view(R, S + N_imp, -1)
+            if train_f and mlp.can_save_forward(run, R * (S + N_imp)):
+                raw_f, ctx.acts_f = mlp.forward_save_bf16(run, R, S + N_imp, rays, z_f)
+                raw_f = raw_f.view(R, S + N_imp, -1)
+            else:
+                raw_f = mlp.forward(run, R, S + N_imp, rays, z_f).view(R, S + N_imp, -1)
             rgb_f, disp_f, acc_f, weights_f, depth_f = ops.raw2outputs_fwd(raw_f, z_f, rays_d, noise_f, white)
             ctx.save_for_backward(rays, z_c, raw_c, z_f, raw_f, noise_c if noise_c is not None else empty,
                                   noise_f if noise_f is not None else empty)
@@ -118,9 +141,13 @@ class RenderRaysFn(Function):
             if d_raw is not None:
                 g_raw_f = g_raw_f + d_raw
             run = net_f if net_f is not None else net_c
-            grads_f = mlp.backward(run, R, S + N_imp, rays, z_f, None, None, g_raw_f.view(R * (S + N_imp), -1))
+            if ctx.acts_f is not None:
+                grads_f = mlp.backward_from_saved(run, R * (S + N_imp), ctx.acts_f, g_raw_f)
+                ctx.acts_f = None
+            else:
+                grads_f = mlp.backward(run, R, S + N_imp, rays, z_f, None, None, g_raw_f.view(R * (S + N_imp), -1))
             g_raw_c = ops.raw2outputs_bwd(raw_c, z_c, rays_d, noise_c, white, d_rgb0, d_disp0, d_acc0, None, d_depth0)
-            grads_c = mlp.backward(net_c, R, S, rays, z_c, None, None, g_raw_c.view(R * S, -1))
+            grads_c = _backward_coarse(ctx, net_c, R, S, rays, z_c, g_raw_c)
             if net_f is None:
                 for k in grads_c:
                     grads_c[k] += grads_f[k]
@@ -129,7 +156,7 @@ class RenderRaysFn(Function):
             g_raw_c = ops.raw2outputs_bwd(raw_c, z_c, rays_d, noise_c, white, d_rgb, d_disp, d_acc, None, d_depth)
             if d_raw is not None:
                 g_raw_c = g_raw_c + d_raw
-            grads_c = mlp.backward(net_c, R, S, rays, z_c, None, None, g_raw_c.view(R * S, -1))
+            grads_c = _backward_coarse(ctx, net_c, R, S, rays, z_c, g_raw_c)
         out = [grads_c[n] for n in named_c]
         if net_f is not None and N_imp > 0:
             out += [grads_f[n] for n, _ in net_f.named_parameters()]

@@ -9,7 +9,10 @@ namespace nerfb {
 constexpr int kTileRows = 128;                 // rows per CTA per tile (UMMA M / 2)
 constexpr int kSuperRows = 512;                // rows per cluster per iteration (2 CTAs x 2 tiles)
 constexpr int kChunkBytes = 16384;             // 128 rows x 64 bf16 (one K chunk of A, or half of a B chunk)
-constexpr int kNS = 4;                         // weight ring slots (= one 256x256 layer per CTA)
+#ifndef NERFB_RING_SLOTS
+#define NERFB_RING_SLOTS 4
+#endif
+constexpr int kNS = NERFB_RING_SLOTS;          // weight ring slots of 16 KB per CTA (4 = one 256x256 layer)
 constexpr int kThreads = 384;                  // warps: 0 loader, 1 mma, 2 tmem, 3 relay, 4..11 epilogue
 constexpr int kEpiThreads = 256;
 #ifndef NERFB_LOAD_PIECES
@@ -41,7 +44,12 @@ constexpr int kSmAct = 0;                      // 2 tiles x 4 chunks
 constexpr int kSmEnc = 2 * 4 * kChunkBytes;    // 131072: gamma(x) / gamma(d) operand chunk
 constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
 constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
-constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
+#ifdef NERFB_EXP_FAKEPAR          // timing experiment only: no parameter block in shared memory (results are garbage)
+constexpr int kSmSig = kSmParams;
+#else
+constexpr int kSmSig = kSmParams + kParamBytes;
+#endif
+constexpr int kSmSigUnused = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
 constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
 constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
 constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;

@@ -190,7 +190,11 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   const int cluster_id = blockIdx.x >> 1;
   const uint32_t sbase = smem_u32(smem);
 
+#ifdef NERFB_EXP_FAKEPAR
+  float* s_par = reinterpret_cast<float*>(smem + kSmEnc);
+#else
   float* s_par = reinterpret_cast<float*>(smem + kSmParams);
+#endif
   float* s_sig = reinterpret_cast<float*>(smem + kSmSig);
   auto bar = [&](int i) -> uint32_t { return sbase + kSmBars + 8 * i; };
   const int B_FULL = 0, B_EMPTY = kNS, B_ACT = 2 * kNS, B_DONE = 2 * kNS + 2, B_ENC = 2 * kNS + 4;
@@ -223,7 +227,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   }
   {
     const float* gpar = reinterpret_cast<const float*>(a.packed + a.param_off);
+#ifndef NERFB_EXP_FAKEPAR
     for (int i = tid; i < kParamFloats; i += kThreads) s_par[i] = __ldg(gpar + i);
+#endif
   }
   if (warp == 2) {
     tmem_alloc<2>(sbase + kSmTmemSlot, 512);
@@ -298,7 +304,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       for (int n = 0; n < total_ops;) {
         const int tile = (cur >> 8) & 0xFF, asrc = (cur >> 16) & 0xFF;
         const uint32_t flags = cur >> 24;
-        const int slot = gl & (kNS - 1);
+        const int slot = gl % kNS;
         bool waited = false;
         if (flags & F_FIRST) {
           const uint32_t cnt = tile ? act_cnt1 : act_cnt0;
@@ -308,7 +314,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           if (lane == 0) tr(1, 0x300 + o);
         }
         if (gl >= confirmed) {
-          if (!ok_w) mbar_wait(bar(B_FULL + slot), (uint32_t)((gl >> 2) & 1), a.watch, 0x400 + o);
+          if (!ok_w) mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x400 + o);
           confirmed = gl + 1;
           waited = true;
         }
@@ -325,7 +331,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int sl = (gl + k) & (kNS - 1);
+              const int sl = (gl + k) % kNS;
               const uint64_t dak = da + (uint64_t)(k * (kChunkBytes >> 4));
               const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + sl * kChunkBytes) >> 4) & 0x3FFF);
               umma_bf16<2>(d_tmem, dak, db, idesc, k == 0 ? 0u : 1u);
@@ -362,7 +368,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           const int tile2 = (cur >> 8) & 0xFF;
           ok_act = ok_w = false;
           if ((cur >> 24) & F_FIRST) ok_act = mbar_try_wait(bar(B_ACT + tile2), (tile2 ? act_cnt1 : act_cnt0) & 1);
-          if (gl >= confirmed) ok_w = mbar_try_wait(bar(B_FULL + (gl & (kNS - 1))), (uint32_t)((gl >> 2) & 1));
+          if (gl >= confirmed) ok_w = mbar_try_wait(bar(B_FULL + (gl % kNS)), (uint32_t)((gl / kNS) & 1));
         }
       }
     }

@@ -252,14 +252,15 @@ def _param_ptrs(named):
     return ptrs
 
 
-def _train_workspace(dev, nrows):
+def _train_workspace(dev, nrows, need_acts=True):
     """(acts, gstore) tile stores for up to nrows samples, cached per device (grown on demand)."""
-    need = (ops.train_store_bytes(nrows, 0), ops.train_store_bytes(nrows, 1))
+    need = (ops.train_store_bytes(nrows, 0) if need_acts else 0, ops.train_store_bytes(nrows, 1))
     ws = _workspaces.get(dev)
     if ws is None or ws[0].numel() < need[0] or ws[1].numel() < need[1]:
+        sizes = (max(need[0], ws[0].numel() if ws else 0), max(need[1], ws[1].numel() if ws else 0))
         ws = None
         _workspaces.pop(dev, None)
-        ws = (torch.empty(need[0], dtype=torch.uint8, device=dev), torch.empty(need[1], dtype=torch.uint8, device=dev))
+        ws = (torch.empty(sizes[0], dtype=torch.uint8, device=dev), torch.empty(sizes[1], dtype=torch.uint8, device=dev))
         _workspaces[dev] = ws
     return ws
 
@@ -294,6 +295,39 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
                               _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), packed, raw_tmp, acts)
         ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore)
         ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs)
+    return grads
+
+
+SAVE_BUDGET_BYTES = int(os.environ.get("NERFB200_SAVE_BUDGET_GB", "24")) << 30
+
+
+def can_save_forward(net, nrows: int) -> bool:
+    """Training forward may keep its layer inputs (5 KB per sample) for the backward instead of
+    recomputing them, when the tile stores of this pass fit the budget."""
+    return (_PRECISION == "bf16" and supports_bf16_backward(net)
+            and ops.train_store_bytes(nrows, 0) + ops.train_store_bytes(nrows, 1) <= SAVE_BUDGET_BYTES)
+
+
+def forward_save_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
+    """Fused forward that also stores every layer input (bf16 operand images) -> (raw, acts)."""
+    dev = net.pts_linears[0].weight.device
+    n = R * S
+    raw = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device=dev)
+    ops.mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed_weights(net), raw, acts)
+    return raw, acts
+
+
+def backward_from_saved(net, nrows: int, acts, d_raw) -> Dict[str, torch.Tensor]:
+    """Parameter gradients from the activations a forward_save_bf16 pass stored (no recompute)."""
+    dev = acts.device
+    grads = {n: torch.zeros_like(p) for n, p in net.named_parameters()}
+    npad = (nrows + 511) // 512 * 512
+    d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
+    d_pad[:nrows].copy_(L.f32c(d_raw).view(-1, 4))
+    _, gstore = _train_workspace(dev, nrows, need_acts=False)
+    ops.mlp_bwd_chain_bf16(nrows, d_pad, packed_weights_bwd(net), acts, gstore)
+    ops.mlp_wgrad_bf16(nrows, acts, gstore, d_pad, _param_ptrs(grads))
     return grads
 
 
