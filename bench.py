@@ -50,6 +50,16 @@ def peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json, written from an `ncu --set full` run of a bench-shaped launch); None if absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    return {"bytes_per_launch": t["dram_bytes"], "launch": t["launch"], "source": t["source"]}
+
+
 def make_args():
     tmp = tempfile.mkdtemp(prefix="nerfb_bench_")
     return types.SimpleNamespace(multires=10, i_embed=0, use_viewdirs=True, multires_views=4,
@@ -299,7 +309,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "nerf_mlp_fwd_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                          "frac_of_burst_peak": achieved / pk["burst"],
                          "kernel_share_of_step": tot_ms / total_ms, "launches_timed": len(mlp_times),
