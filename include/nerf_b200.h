@@ -211,8 +211,13 @@ int nerfb_umma_selftest_mn(int N, int K, const float* At, const float* Bt, float
 /* Probe (tools/probe_bulk.py): cycles per chunk of the 1-D bulk-copy path, per CTA, ring of `depth`. */
 int nerfb_bulk_probe(const void* src, int src_bytes, int nchunks, int chunk_bytes, int pieces, int depth,
                      int nblocks, long long* out_cycles, void* stream);
+/* Probe (tools/probe_contention.py): bulk-copy stream concurrent with UMMAs (mode 0 none, 1 SS, 2 TS) and
+ * sts_warps warps of shared-memory stores; out[4*block + {0,1,2,3}] = cycles/chunk, cycles/MMA, #MMAs, #stores. */
+int nerfb_contention_probe(const void* src, int src_bytes, int nchunks, int mode, int sts_warps, int nblocks,
+                           long long* out, void* stream);
 /* Debug: when dev_buf != NULL, block 0 of the fused MLP kernel records a clock64 timeline
- * (3 regions x 4096 entries: loader, MMA issuer, epilogue; entry = tag<<44 | cycles).
+ * (8 regions x 4096 entries: loader, MMA issuer, epilogue, relay/observer of the leader CTA, then of the peer;
+ * entry = tag<<44 | cycles).
  * Pass NULL to switch tracing off. */
 int nerfb_set_trace(long long* dev_buf);
 /* Host pointer to the 8 x u64 watchdog record the tensor-core kernels write

@@ -54,7 +54,8 @@ constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
 constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
 constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
 constexpr int kSmOps = kSmTmemSlot + 16;                 // copy of Sched::ops (u32 each)
-constexpr int kSmemBytes = kSmOps + 84 * 4;
+constexpr int kSmLoads = kSmOps + 84 * 4;                // copy of Sched::loads (2 x u32 each)
+constexpr int kSmemBytes = kSmLoads + 44 * 8;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 
 // ---------------------------------------------------- training tile stores

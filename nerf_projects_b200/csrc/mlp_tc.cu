@@ -24,6 +24,7 @@
 //     layer activations;
 //   * every barrier wait is bounded by a watchdog (tc05.cuh).
 #include <cstdlib>
+#include <cuda.h>
 #include "common.cuh"
 #include "tc05.cuh"
 #include "mlp_layout.cuh"
@@ -37,8 +38,10 @@ tc05::Watch get_watch();  // umma_selftest.cu
 // A static program shared by the three asynchronous roles.  Generated on the
 // host (build_schedule) and passed by value.
 struct LoadEnt { uint32_t off; uint32_t bytes; };          // blob offset of the chunk, bytes per CTA
-enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16,
-               F_BLOCK4 = 32 };   // this op and the next 3: one tile's pass over 4 resident chunks, issued back to back
+enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16 };
+// One op = 4 MMAs (K = 64) of one tile over one weight chunk.  Consecutive ops of the same tile and layer form a
+// BLOCK (one pass of the tile over the layer): `tile` carries the block length in its high nibble on the block's
+// first op; the MMA issuer handles a block as one unit with minimal work between its chunks.
 struct OpEnt { uint8_t load, tile, asrc, flags; };          // asrc 0..3 = act chunk, 4 = enc
 struct Sched {
   int nloads, nops, nlayers;
@@ -60,14 +63,17 @@ static void build_schedule(bool vd, Sched& s) {
   auto add_op = [&](uint8_t load, int tile, int asrc, int flags) {
     s.ops[s.nops++] = OpEnt{load, (uint8_t)tile, (uint8_t)asrc, (uint8_t)flags};
   };
+  int blk_first[48], blk_count[48], nblk = 0;
+  auto block = [&](int first, int count) { blk_first[nblk] = first; blk_count[nblk++] = count; };
   // plain K=256 layer: chunks id0..id0+3, both tiles pass over the resident layer
   auto plain = [&](int id0, bool n128) {
     uint8_t l[4];
     for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
     const int f = n128 ? F_N128 : 0;
+    block(s.nops, 4);
     for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
-    for (int k = 0; k < 4; ++k)
-      add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST | F_BLOCK4 : 0) | (k == 3 ? F_LAST : 0));
+    block(s.nops, 4);
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
   };
   // layer with an extra K=64 chunk read from the enc buffer (skip concat / view concat):
   // tile A consumes it first, tile B last, so the 4-slot ring never needs 5 live chunks.
@@ -77,14 +83,18 @@ static void build_schedule(bool vd, Sched& s) {
     uint8_t l[4];
     for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
     const uint8_t g2 = add_load(id_enc, n128);
+    block(s.nops, 5);
     add_op(g, 0, 4, f | F_FIRST | F_REL_SLOT | F_REL_ENC);
     for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 3 ? F_LAST : 0));
-    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST | F_BLOCK4 : 0));
+    block(s.nops, 5);
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0));
     add_op(g2, 1, 4, f | F_LAST | F_REL_SLOT | F_REL_ENC);
   };
   {  // layer 0: K = 64 (gamma(x)), one chunk used by both tiles
     const uint8_t g0 = add_load(0, false);
+    block(s.nops, 1);
     add_op(g0, 0, 4, F_FIRST | F_LAST | F_REL_ENC);
+    block(s.nops, 1);
     add_op(g0, 1, 4, F_FIRST | F_LAST | F_REL_ENC | F_REL_SLOT);
   }
   for (int l = 1; l <= 4; ++l) plain(1 + 4 * (l - 1), false);
@@ -95,6 +105,7 @@ static void build_schedule(bool vd, Sched& s) {
     plain(30, false);               // feature_linear
     with_enc(34, 35, true);         // views_linears[0]: [feature | gamma(d)], N = 128
   }
+  for (int i = 0; i < nblk; ++i) s.ops[blk_first[i]].tile |= (uint8_t)(blk_count[i] << 4);
 }
 
 // backward chain: d_hv -> d_feature -> d_h7 -> ... -> d_h0 with transposed weights
@@ -108,18 +119,24 @@ static void build_schedule_bwd(Sched& s) {
   auto add_op = [&](uint8_t load, int tile, int asrc, int flags) {
     s.ops[s.nops++] = OpEnt{load, (uint8_t)tile, (uint8_t)asrc, (uint8_t)flags};
   };
+  int blk_first[48], blk_count[48], nblk = 0;
+  auto block = [&](int first, int count) { blk_first[nblk] = first; blk_count[nblk++] = count; };
   {  // views^T: K = 128 (two chunks)
     const uint8_t l0 = add_load(0), l1 = add_load(1);
+    block(s.nops, 2);
     add_op(l0, 0, 0, F_FIRST); add_op(l1, 0, 1, F_LAST);
+    block(s.nops, 2);
     add_op(l0, 1, 0, F_FIRST | F_REL_SLOT); add_op(l1, 1, 1, F_LAST | F_REL_SLOT);
   }
   for (int j = 1; j <= 8; ++j) {
     uint8_t l[4];
     for (int k = 0; k < 4; ++k) l[k] = add_load(2 + 4 * (j - 1) + k);
+    block(s.nops, 4);
     for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
-    for (int k = 0; k < 4; ++k)
-      add_op(l[k], 1, k, F_REL_SLOT | (k == 0 ? F_FIRST | F_BLOCK4 : 0) | (k == 3 ? F_LAST : 0));
+    block(s.nops, 4);
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, F_REL_SLOT | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
   }
+  for (int i = 0; i < nblk; ++i) s.ops[blk_first[i]].tile |= (uint8_t)(blk_count[i] << 4);
 }
 
 struct MlpArgs {
@@ -181,7 +198,8 @@ __device__ __forceinline__ void store_row32(uint8_t* chunk, int row, int unit0, 
 // -------------------------------------------------------------- kernel
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc) {
+nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc,
+                const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64) {
   constexpr bool SAVE = (MODE == MODE_FWD_SAVE);
   constexpr bool BWD = (MODE == MODE_BWD);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -200,17 +218,20 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   const int B_FULL = 0, B_EMPTY = kNS, B_ACT = 2 * kNS, B_DONE = 2 * kNS + 2, B_ENC = 2 * kNS + 4;
 
   if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xA11, sbase, 0);
-  const bool tracing = (a.trace != nullptr) && blockIdx.x == 0;
+  // debug timeline: blocks 0 (leader) and 1 (peer) of cluster 0; 4 regions each: loader, MMA, epilogue, relay/observer
+  const bool tracing = (a.trace != nullptr) && blockIdx.x < 2;
+  const int tr_base = blockIdx.x * 4;
   int tr_n = 0;
   auto tr = [&](int region, int tag) {
-    if (tracing && tr_n < kTraceLen) a.trace[region * kTraceLen + tr_n++] = ((long long)tag << 44) | (clock64() & 0xFFFFFFFFFFFll);
+    if (tracing && tr_n < kTraceLen) a.trace[(tr_base + region) * kTraceLen + tr_n++] = ((long long)tag << 44) | (clock64() & 0xFFFFFFFFFFFll);
   };
 
   // ---- one-time setup
   if (tid == 0) {
     for (int s = 0; s < kNS; ++s) {
-      // leader: own loader (arrive.expect_tx) + the peer's relay (remote arrive) -> ONE barrier per slot
-      mbar_init(bar(B_FULL + s), rank == 0 ? 2 : 1);
+      // ONE barrier per slot, in the leader CTA: its loader arrives with expect_tx for BOTH halves and the
+      // tensor-map copies of both CTAs complete their bytes on it (.cta_group::2) -- no relay hop
+      mbar_init(bar(B_FULL + s), 1);
       mbar_init(bar(B_EMPTY + s), 1);
     }
     mbar_init(bar(B_ACT + 0), 2);
@@ -220,6 +241,11 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     mbar_init(bar(B_ENC), 1);
     fence_barrier_init();
   }
+  // The schedule tables are read from SHARED memory in the hot loops: a dynamically indexed read of the
+  // kernel-parameter constant bank misses the (tiny, instruction-shared) constant cache almost every time here,
+  // ~500 cycles per table entry in the loader and the MMA issuer (timeline in profiles/).
+  for (int i = tid; i < sc.nloads; i += kThreads)
+    reinterpret_cast<uint2*>(smem + kSmLoads)[i] = make_uint2(sc.loads[i].off, sc.loads[i].bytes);
   for (int i = tid; i < sc.nops; i += kThreads) {
     const OpEnt e = sc.ops[i];
     reinterpret_cast<uint32_t*>(smem + kSmOps)[i] =
@@ -241,38 +267,40 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kSmTmemSlot);
 
   const int niter = (a.nst - cluster_id + a.nclusters - 1) / a.nclusters;   // super-tiles of this cluster
+  if (lane == 0 && (warp == 0 || warp == 1 || warp == 4)) tr(warp == 0 ? 0 : (warp == 1 ? 1 : 2), 0xFFF);  // clock alignment marker
 
   if (warp == 0) {
     // ===================== weight loader (both CTAs: own half of every chunk)
     if (lane == 0) {
       long long gl = 0;
+      const uint32_t full_leader = mapa(bar(B_FULL), 0);      // shared::cluster address of the leader's w_full[0]
       for (int it = 0; it < niter; ++it) {
         for (int q = 0; q < sc.nloads; ++q, ++gl) {
           const int slot = (int)(gl % kNS);
           if (gl >= kNS) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((gl / kNS) + 1) & 1), a.watch, 0x100 + q);
           tr(0, 0x100 + q);
-          const LoadEnt le = sc.loads[q];
-          mbar_arrive_expect_tx(bar(B_FULL + slot), le.bytes);
-          // several smaller bulk copies per chunk: more requests in flight -> lower completion latency
-          const uint32_t piece = le.bytes / kLoadPieces;
-#pragma unroll
-          for (int pc = 0; pc < kLoadPieces; ++pc)
-            bulk_g2s(sbase + kSmRing + slot * kChunkBytes + pc * piece,
-                     a.packed + le.off + (size_t)rank * le.bytes + pc * piece, piece, bar(B_FULL + slot));
+          const uint2 le2 = reinterpret_cast<const uint2*>(smem + kSmLoads)[q];
+          const LoadEnt le{le2.x, le2.y};
+          if (rank == 0) mbar_arrive_expect_tx(bar(B_FULL + slot), 2 * le.bytes);
+          // my half of the chunk = rows [row0, row0 + bytes/128) of the blob viewed as [rows][128 B]
+          const int row0 = (int)((le.off + rank * le.bytes) >> 7);
+          tma_load_2d_cg2(sbase + kSmRing + slot * kChunkBytes, le.bytes == (uint32_t)kChunkBytes ? &tm128 : &tm64,
+                          full_leader + 8 * slot, 0, row0);
+          tr(0, 0xA00 + q);
         }
       }
     }
   } else if (warp == 3) {
-    // ===================== relay (peer CTA): tell the leader my half has landed
-    if (lane == 0 && rank == 1) {
+    // ===================== (idle; debug observer of the leader's weight barriers when tracing)
+    if (lane == 0 && rank == 0 && tracing) {
+      // debug observer (leader's otherwise idle warp): when does each weights barrier really complete?
       long long gl = 0;
-      for (int it = 0; it < niter; ++it) {
+      for (int it = 0; it < niter; ++it)
         for (int q = 0; q < sc.nloads; ++q, ++gl) {
           const int slot = (int)(gl % kNS);
-          mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x200 + q);
-          mbar_arrive_remote(bar(B_FULL + slot), 0);
+          mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x280 + q);
+          tr(3, 0xB00 + q);
         }
-      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA)
@@ -284,68 +312,52 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     //    waterfall loop of 7 R2UR.BROADCAST (~170 cycles per MMA instead of 128);
     //  * ONE weights barrier per slot, no wait at all for the second tile's pass over a
     //    resident chunk, and the barrier probes of op o+1 are issued BEFORE the MMAs of op o.
-    if (rank == 0) {
+    // ONE elected lane runs the whole persistent loop (the compiler then knows every operand is uniform and
+    // keeps descriptors in uniform registers); the other lanes wait at the final __syncwarp.  The unit of
+    // work is a BLOCK -- one tile's pass over the chunks of a layer: between two chunks of a block there is
+    // only a table read (shared memory), at most one barrier probe, a few descriptor adds, 4 UTCHMMA and
+    // the commits.  (The per-op bookkeeping of the first version cost ~500 cycles between MMA groups --
+    // ~100 dependent instructions on one warp -- and idled the tensor core in every first-tile pass.)
+    if (rank == 0 && elect_one()) {
       // the whole TMEM (512 columns) is allocated, so its base address is 0: keep it a constant
       if (tmem_base != 0) watchdog_fire(a.watch, 0xA12, tmem_base, 0);
       const uint32_t idesc256 = make_idesc_bf16(256, 256), idesc128 = make_idesc_bf16(256, 128);
       const uint64_t desc_hi = make_sdesc_sw128(0);            // everything but the start address
+      const uint32_t* s_ops = reinterpret_cast<const uint32_t*>(smem + kSmOps);
+      const int nops = sc.nops, nloads = sc.nloads;
       uint32_t act_cnt0 = 0, act_cnt1 = 0;
       int confirmed = 0;                                       // loads [0, confirmed) are known to have landed
-      const int nops = sc.nops, nloads = sc.nloads;
-      const int total_ops = niter * nops;
-      auto fetch = [&](int o) -> uint32_t {
-        const OpEnt e = sc.ops[o];                             // uniform index -> ULDC from the param bank
-        return (uint32_t)e.load | ((uint32_t)e.tile << 8) | ((uint32_t)e.asrc << 16) | ((uint32_t)e.flags << 24);
-      };
-      uint32_t cur = fetch(0);
-      int gl = (int)(cur & 0xFF);
-      bool ok_act = false, ok_w = false;
-      int o = 0, gl0 = 0;
-      for (int n = 0; n < total_ops;) {
-        const int tile = (cur >> 8) & 0xFF, asrc = (cur >> 16) & 0xFF;
-        const uint32_t flags = cur >> 24;
-        const int slot = gl % kNS;
-        bool waited = false;
-        if (flags & F_FIRST) {
-          const uint32_t cnt = tile ? act_cnt1 : act_cnt0;
-          if (!ok_act) mbar_wait(bar(B_ACT + tile), cnt & 1, a.watch, 0x300 + o);
-          if (tile) ++act_cnt1; else ++act_cnt0;
-          waited = true;
-          if (lane == 0) tr(1, 0x300 + o);
-        }
-        if (gl >= confirmed) {
-          if (!ok_w) mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x400 + o);
-          confirmed = gl + 1;
-          waited = true;
-        }
-        if (lane == 0) tr(1, 0x500 + o);
-        if (waited) tc_fence_after();
-        const uint32_t d_tmem = (uint32_t)tile * 256u;
-        const uint32_t idesc = (flags & F_N128) ? idesc128 : idesc256;
-        const uint32_t a_addr = (asrc < 4) ? (sbase + kSmAct + (tile * 4 + asrc) * kChunkBytes) : (sbase + kSmEnc);
-        const uint64_t da = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-        int adv;
-        if (flags & F_BLOCK4) {
-          // second tile's pass: the 4 chunks (loads gl..gl+3) are resident and already confirmed
-          const uint32_t last_flags = (uint32_t)sc.ops[o + 3].flags;
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int sl = (gl + k) % kNS;
-              const uint64_t dak = da + (uint64_t)(k * (kChunkBytes >> 4));
-              const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + sl * kChunkBytes) >> 4) & 0x3FFF);
-              umma_bf16<2>(d_tmem, dak, db, idesc, k == 0 ? 0u : 1u);
-              umma_bf16<2>(d_tmem, dak + 2, db + 2, idesc, 1u);
-              umma_bf16<2>(d_tmem, dak + 4, db + 4, idesc, 1u);
-              umma_bf16<2>(d_tmem, dak + 6, db + 6, idesc, 1u);
-              umma_commit<2>(bar(B_EMPTY + sl));
-            }
-            if (last_flags & F_LAST) umma_commit<2>(bar(B_DONE + tile));
+      int gl0 = 0;
+      for (int it = 0; it < niter; ++it, gl0 += nloads) {
+        for (int o = 0; o < nops;) {
+          uint32_t e = s_ops[o];
+          const int tile = (e >> 8) & 0xF, blk = (e >> 12) & 0xF;
+          if (blk == 0) watchdog_fire(a.watch, 0xA13, (uint32_t)o, e);
+          if ((e >> 24) & F_FIRST) {
+            const uint32_t cnt = tile ? act_cnt1 : act_cnt0;
+            mbar_wait(bar(B_ACT + tile), cnt & 1, a.watch, 0x300 + o);
+            if (tile) ++act_cnt1; else ++act_cnt0;
+            tc_fence_after();
+            tr(1, 0x300 + o);
           }
-          adv = 4;
-        } else {
-          const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + slot * kChunkBytes) >> 4) & 0x3FFF);
-          if (elect_one()) {
+          const uint32_t d_tmem = (uint32_t)tile * 256u;
+          const uint32_t act_base = sbase + kSmAct + tile * 4 * kChunkBytes;
+          for (int k = 0; k < blk; ++k) {
+            const uint32_t en = (k + 1 < blk) ? s_ops[o + k + 1] : 0u;   // next entry: its LDS overlaps the MMA issue
+            const int asrc = (e >> 16) & 0xFF;
+            const uint32_t flags = e >> 24;
+            const int gl = gl0 + (int)(e & 0xFF);
+            const int slot = gl % kNS;
+            if (gl >= confirmed) {
+              mbar_wait(bar(B_FULL + slot), (uint32_t)((gl / kNS) & 1), a.watch, 0x400 + o + k);
+              confirmed = gl + 1;
+              tc_fence_after();
+              tr(1, 0x500 + o + k);
+            }
+            const uint32_t a_addr = (asrc < 4) ? (act_base + asrc * kChunkBytes) : (sbase + kSmEnc);
+            const uint64_t da = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+            const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + slot * kChunkBytes) >> 4) & 0x3FFF);
+            const uint32_t idesc = (flags & F_N128) ? idesc128 : idesc256;
             umma_bf16<2>(d_tmem, da, db, idesc, (flags & F_FIRST) ? 0u : 1u);
             umma_bf16<2>(d_tmem, da + 2, db + 2, idesc, 1u);
             umma_bf16<2>(d_tmem, da + 4, db + 4, idesc, 1u);
@@ -353,25 +365,14 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             if (flags & F_REL_SLOT) umma_commit<2>(bar(B_EMPTY + slot));
             if (flags & F_REL_ENC) umma_commit<2>(bar(B_ENC));
             if (flags & F_LAST) umma_commit<2>(bar(B_DONE + tile));
+            e = en;
           }
-          adv = 1;
-        }
-        __syncwarp();
-        if (lane == 0) tr(1, 0x600 + o);
-        // ---- next op: table entry and (while the last MMA above is still executing) barrier probes
-        n += adv;
-        o += adv;
-        if (o >= nops) { o -= nops; gl0 += nloads; }
-        if (n < total_ops) {
-          cur = fetch(o);
-          gl = gl0 + (int)(cur & 0xFF);
-          const int tile2 = (cur >> 8) & 0xFF;
-          ok_act = ok_w = false;
-          if ((cur >> 24) & F_FIRST) ok_act = mbar_try_wait(bar(B_ACT + tile2), (tile2 ? act_cnt1 : act_cnt0) & 1);
-          if (gl >= confirmed) ok_w = mbar_try_wait(bar(B_FULL + (gl % kNS)), (uint32_t)((gl / kNS) & 1));
+          tr(1, 0x600 + o);
+          o += blk;
         }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue / encoding warps
     const int et = tid - 128;
@@ -877,6 +878,45 @@ extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs
   return check_launch("pack_weights_kernel");
 }
 
+// Tensor maps over a packed weight blob viewed as [rows][128 B] uint8 (images are pre-swizzled, so SWIZZLE_NONE):
+// box = 128 rows (one 16 KB chunk half) or 64 rows (views layer).  Cached per blob address.
+struct BlobMaps { const void* ptr; size_t bytes; CUtensorMap tm128, tm64; };
+static int get_blob_maps(const void* blob, size_t bytes, const BlobMaps** out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static BlobMaps cache[8];
+  static int ncache = 0, victim = 0;
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].ptr == blob && cache[i].bytes == bytes) { *out = &cache[i]; return NERFB_OK; }
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NERFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    NERFB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    encode = (EncodeFn)fn;
+  }
+  BlobMaps m{};
+  m.ptr = blob; m.bytes = bytes;
+  const cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t estr[2] = {1, 1};
+  for (int k = 0; k < 2; ++k) {
+    const cuuint32_t box[2] = {128, k == 0 ? 128u : 64u};
+    const CUresult r = encode(k == 0 ? &m.tm128 : &m.tm64, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NERFB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for blob %p, %zu bytes", (int)r, blob, bytes);
+  }
+  int slot;
+  if (ncache < 8) slot = ncache++;
+  else { slot = victim; victim = (victim + 1) % 8; }
+  cache[slot] = m;
+  *out = &cache[slot];
+  return NERFB_OK;
+}
+
 static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   static Sched sched_vd, sched_novd, sched_bwd;
   static bool init = false;
@@ -903,14 +943,17 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
+  const BlobMaps* maps = nullptr;
+  const size_t blob_bytes = (size_t)a.param_off + kParamBytes;
+  if (int rc = get_blob_maps(a.packed, blob_bytes, &maps)) return rc;
   if (mode == MODE_FWD) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd));
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
     return check_launch("nerf_mlp_kernel<FWD>");
   } else if (mode == MODE_FWD_SAVE) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd));
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64));
     return check_launch("nerf_mlp_kernel<FWD_SAVE>");
   }
-  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd));
+  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64));
   return check_launch("nerf_mlp_kernel<BWD>");
 }
 

@@ -203,6 +203,102 @@ bulk_probe_kernel(const uint8_t* __restrict__ src, int src_bytes, int nchunks, i
   }
 }
 
+
+// Probe 2: the bulk-copy stream of bulk_probe_kernel running CONCURRENTLY with back-to-back UMMAs on static
+// operands (mode 0: no MMA, 1: SS form -- A and B from shared memory, 2: TS form -- A from tensor memory) and,
+// optionally, 8 warps of 16-byte shared-memory stores (the epilogue's store traffic).  Reports cycles per
+// 16 KB chunk and cycles per MMA (M=128, N=256, K=16, cta_group::1).  Answers: who competes for shared memory?
+__global__ void __launch_bounds__(320, 1)
+contention_probe_kernel(const uint8_t* __restrict__ src, int src_bytes, int nchunks, int mode, int sts_warps,
+                        long long* __restrict__ out, Watch watch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[8];
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int stop_flag;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kChunk = 16384, kDepth = 4;
+  // layout: [A 16 KB][B 32 KB][ring 4 x 16 KB][sts scratch 32 KB]
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 16384;
+  uint8_t* ring = smem + 49152;
+  uint8_t* scratch = ring + kDepth * kChunk;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_barrier_init();
+    stop_flag = 0;
+  }
+  for (int i = tid; i < 49152 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3c003c00u, 0, 0x3c003c00u, 0);
+  fence_proxy_async_smem();
+  if (warp == 1) { tmem_alloc<1>(smem_u32(&tmem_slot), 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t base = smem_u32(ring);
+      long long t0 = 0, lat_sum = 0;
+      const int warm = 16;
+      for (int i = 0; i < nchunks + kDepth; ++i) {
+        const int slot = i % kDepth;
+        if (i >= kDepth) mbar_wait(smem_u32(&bars[slot]), (uint32_t)(((i / kDepth) - 1) & 1), watch, 0x78);
+        if (i == warm) t0 = clock64();
+        if (i < nchunks) {
+          const uint32_t off = ((uint32_t)i * kChunk + blockIdx.x * 4096u) % (uint32_t)(src_bytes - kChunk);
+          mbar_arrive_expect_tx(smem_u32(&bars[slot]), kChunk);
+          bulk_g2s(base + slot * kChunk, src + (off & ~15u), kChunk, smem_u32(&bars[slot]));
+        }
+      }
+      out[blockIdx.x * 4 + 0] = (clock64() - t0) / (nchunks + kDepth - warm);
+      (void)lat_sum;
+      stop_flag = 1;
+    }
+  } else if (warp == 1) {
+    if (mode != 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256);
+      const uint64_t da = make_sdesc_sw128(smem_u32(sA)), db = make_sdesc_sw128(smem_u32(sB));
+      long long n = 0;
+      const long long t0 = clock64();
+      uint32_t phase = 0;
+      while (!stop_flag) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (mode == 1) umma_bf16<1>(tmem_base, da + (uint64_t)((k & 3) * 2), db + (uint64_t)((k & 3) * 2), idesc, 1u);
+            else umma_bf16_ts<1>(tmem_base, tmem_base + 256 + (k & 3) * 8, db + (uint64_t)((k & 3) * 2), idesc, 1u);
+          }
+          umma_commit<1>(smem_u32(&bars[4]));
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(&bars[4]), phase, watch, 0x79);
+        phase ^= 1;
+        n += 16;
+      }
+      if (lane == 0) { out[blockIdx.x * 4 + 1] = (clock64() - t0) / (n > 0 ? n : 1); out[blockIdx.x * 4 + 2] = n; }
+    }
+  } else if (warp - 2 < sts_warps) {
+    // epilogue-like store traffic: every thread writes 16 B per iteration, conflict-free rows
+    uint4 v = make_uint4(tid, tid, tid, tid);
+    uint8_t* p = scratch + (size_t)(tid & 255) * 128;
+    long long n = 0;
+    while (!stop_flag) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p + (((i ^ tid) & 7) << 4))), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+        v.x += 1;
+      }
+      n += 8;
+    }
+    if (tid == 64) out[blockIdx.x * 4 + 3] = n;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 512);
+}
+
 }  // namespace nerfb
 
 using namespace nerfb;
@@ -262,4 +358,16 @@ extern "C" int nerfb_bulk_probe(const void* src, int src_bytes, int nchunks, int
   bulk_probe_kernel<<<nblocks, 32, smem, as_stream(stream)>>>((const uint8_t*)src, src_bytes, nchunks, chunk_bytes,
                                                              pieces, depth, out_cycles, w);
   return check_launch("bulk_probe_kernel");
+}
+
+extern "C" int nerfb_contention_probe(const void* src, int src_bytes, int nchunks, int mode, int sts_warps, int nblocks,
+                                      long long* out, void* stream) {
+  NERFB_REQUIRE(src && out && src_bytes > 65536 && nchunks > 64 && mode >= 0 && mode <= 2 && sts_warps >= 0 &&
+                    sts_warps <= 8, "nerfb_contention_probe: bad arguments");
+  const size_t smem = 49152 + 4 * 16384 + 32768 + 1024;
+  tc05::Watch w = get_watch();
+  NERFB_CUDA(cudaFuncSetAttribute(contention_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  contention_probe_kernel<<<nblocks, 320, smem, as_stream(stream)>>>((const uint8_t*)src, src_bytes, nchunks, mode,
+                                                                     sts_warps, out, w);
+  return check_launch("contention_probe_kernel");
 }

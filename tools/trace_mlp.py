@@ -16,28 +16,43 @@ z = (torch.rand(R, S, generator=g) * 4 + 2).sort(-1)[0].cuda()
 for _ in range(2):
     mlp.forward_bf16(net, R, S, rays, z)
 torch.cuda.synchronize()
-buf = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
 _lib.load().nerfb_set_trace(buf.data_ptr())
 mlp.forward_bf16(net, R, S, rays, z)
 torch.cuda.synchronize()
 _lib.load().nerfb_set_trace(None)
-b = buf.cpu().numpy().reshape(3, 4096)
-ev = []
-for region, name in enumerate(("LOAD", "MMA", "EPI")):
+b = buf.cpu().numpy().reshape(8, 4096)
+MASK = (1 << 44) - 1
+# clock alignment: every traced thread records tag 0xFFF right after the cluster barrier; shift the peer's clock
+# so that its marker coincides with the leader's
+def marker(region):
     for v in b[region]:
-        if v == 0: continue
-        ev.append((int(v) & ((1 << 44) - 1), name, int(v) >> 44))
+        if v and (int(v) >> 44) == 0xFFF:
+            return int(v) & MASK
+    return None
+m0 = marker(0)
+shift = {}
+m4 = marker(4)
+for region in range(8):
+    shift[region] = (m0 - m4) if region >= 4 else 0
+ev = []
+names = ("LOAD", "MMA", "EPI", "OBS", "pLOAD", "pMMA", "pEPI", "pRELAY")
+for region, name in enumerate(names):
+    for v in b[region]:
+        if v == 0 or (int(v) >> 44) == 0xFFF:
+            continue
+        ev.append(((int(v) & MASK) + shift[region], name, int(v) >> 44))
 ev.sort()
-t0 = ev[0][0]
-# print iterations 2..3 (steady state): find MMA op 0 act-wait events
 starts = [t for t, n, tag in ev if n == "MMA" and tag == 0x300]
 lo, hi = starts[2], starts[4]
 print("iteration length (cycles):", [starts[i + 1] - starts[i] for i in range(len(starts) - 1)][:8])
 last = {}
 for t, n, tag in ev:
-    if t < lo or t >= hi: continue
+    if t < lo or t >= hi:
+        continue
     kind = tag >> 8
-    desc = {1: "load issued q=%d", 3: "act_ready waited op=%d", 5: "weights ready op=%d", 6: "issued+commits op=%d",
-            7: "mma_done waited l,t=%d", 8: "epilogue end l,t=%d", 9: "signalled t=%d"}[kind] % (tag & 0xFF)
-    print(f"{t - lo:8d}  +{t - last.get(n, t):6d}  {n:4s} {desc}")
+    desc = {1: "load issued q=%d", 2: "relay: own full seen, arrive sent q=%d", 3: "act_ready waited op=%d",
+            5: "weights ready op=%d", 6: "issued+commits op=%d", 7: "mma_done waited l,t=%d", 8: "epilogue end l,t=%d",
+            9: "signalled t=%d", 10: "load copies issued q=%d", 11: "OBSERVER: weights barrier complete q=%d"}[kind] % (tag & 0xFF)
+    print(f"{t - lo:8d}  +{t - last.get(n, t):6d}  {n:6s} {desc}")
     last[n] = t
