@@ -44,6 +44,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "nerf_b200.h"))
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    # experiments: NERFB_SRC_OVERRIDE_DIR holds alternative versions of some sources (A/B against an older kernel)
+    over = os.environ.get("NERFB_SRC_OVERRIDE_DIR")
+    if over:
+        srcs = [os.path.join(over, os.path.basename(p)) if os.path.exists(os.path.join(over, os.path.basename(p))) else p
+                for p in srcs]
     nvcc = _nvcc()
     objs, jobs = [], []
     for src in srcs:

@@ -153,6 +153,12 @@ struct MlpArgs {
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
 };
 constexpr int kTraceLen = 4096;
+// training tile stores: bulk (TMA) copies out of the activation buffers (default), or 16-byte stores from the
+// epilogue registers (measured: forward+save 1.69 ms vs 1.02 ms, chain 2.09 vs 1.66 ms -- kept for reference only)
+#ifndef NERFB_BULK_SAVE
+#define NERFB_BULK_SAVE 1
+#endif
+constexpr bool kBulkSave = NERFB_BULK_SAVE != 0;
 static long long* g_trace = nullptr;
 
 // ------------------------------------------------------------- encoding
@@ -394,11 +400,11 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     auto publish = [&](int t, bool signal, uint8_t* gdst, int npanels) {
       tc_fence_before();
       fence_proxy_async_smem();
-      if ((SAVE || BWD) && et == 0) bulk_wait_read0();
+      if (kBulkSave && (SAVE || BWD) && et == 0) bulk_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0) {
         if (signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
-        if ((SAVE || BWD) && gdst != nullptr) {
+        if (kBulkSave && (SAVE || BWD) && gdst != nullptr) {
           for (int pnl = 0; pnl < npanels; ++pnl)
             bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
           bulk_commit();
@@ -520,6 +526,8 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               const int col0 = 128 * hh + 32 * b;
 #ifndef NERFB_EXP_NOSTS
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+              if (SAVE && !kBulkSave)     // training store straight from registers (same image as the smem operand)
+                store_row32(gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat) + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
 #else
               if (w[0] == 0x12345678u) store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
 #endif
@@ -649,6 +657,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               o[i] = pack_bf16x2(g0, g1) & bf16x2_nonzero_mask(mm[i]);
             }
             *reinterpret_cast<uint4*>(act_t + hh * kChunkBytes + off) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (!kBulkSave) *reinterpret_cast<uint4*>(gtile[t] + kGHv + hh * kPanel + off) = make_uint4(o[0], o[1], o[2], o[3]);
           }
           publish(t, true, gtile[t] + kGHv, 2);
         }
@@ -666,7 +675,12 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               for (int i = 0; i < 4; ++i)
                 dst[i] = __ldg(reinterpret_cast<const uint4*>(pp + sw128_offset(row, ((col0 & 63) >> 3) + i)));
             };
-            if (j > 0) { load_mask(0, hm[0]); load_mask(1, hm[1]); }
+#ifdef NERFB_EXP_NOMASK
+            const bool use_mask = false;
+#else
+            const bool use_mask = j > 0;
+#endif
+            if (use_mask) { load_mask(0, hm[0]); load_mask(1, hm[1]); }
             // pull the NEXT layer's mask tile (64 KB) of this tile into L2 a whole layer ahead
             if (et == 0 && j + 1 < sc.nlayers) bulk_prefetch_l2(ftile[t] + kFH + (m - 1) * 4 * kPanel, 4 * kPanel);
             mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
@@ -694,7 +708,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1]));
               }
-              if (j > 0) {
+              if (use_mask) {
                 const uint4 (&mk)[4] = hm[b & 1];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -707,6 +721,8 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               }
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+              if (!kBulkSave)
+                store_row32(gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel) + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
             }
             if (et == 0) tr(2, 0x800 + j * 2 + t);
             uint8_t* gdst = gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);

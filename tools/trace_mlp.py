@@ -13,12 +13,32 @@ g = torch.Generator().manual_seed(0)
 rays = torch.cat([torch.randn(R, 3, generator=g), torch.randn(R, 3, generator=g), torch.full((R, 1), 2.), torch.full((R, 1), 6.),
                   torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)], -1).cuda()
 z = (torch.rand(R, S, generator=g) * 4 + 2).sort(-1)[0].cuda()
+MODE = sys.argv[1] if len(sys.argv) > 1 else "fwd"      # fwd | save | chain
+from nerf_projects_b200 import ops
+n = R * S
+if MODE != "fwd":
+    R = 4096; n = R * S
+    rays, z = rays[:R].contiguous(), z[:R].contiguous()
+    acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device="cuda")
+    gstore = torch.empty(ops.train_store_bytes(n, 1), dtype=torch.uint8, device="cuda")
+    raw = torch.empty(n, 4, device="cuda")
+    d_pad = torch.randn((n + 511) // 512 * 512, 4, device="cuda")
+    packed, packed_bwd = mlp.packed_weights(net), mlp.packed_weights_bwd(net)
+def run():
+    if MODE == "fwd":
+        mlp.forward_bf16(net, R, S, rays, z)
+    elif MODE == "save":
+        ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts)
+    else:
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore)
+if MODE == "chain":
+    ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts)
 for _ in range(2):
-    mlp.forward_bf16(net, R, S, rays, z)
+    run()
 torch.cuda.synchronize()
 buf = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
 _lib.load().nerfb_set_trace(buf.data_ptr())
-mlp.forward_bf16(net, R, S, rays, z)
+run()
 torch.cuda.synchronize()
 _lib.load().nerfb_set_trace(None)
 b = buf.cpu().numpy().reshape(8, 4096)
