@@ -248,14 +248,15 @@ def main():
 
         def step_e2e():
             for f in range(world):
-                ro = host_rays[f][0].to(dev, non_blocking=True)
-                rd = host_rays[f][1].to(dev, non_blocking=True)
                 if world == 1:
+                    ro = host_rays[f][0].to(dev, non_blocking=True)
+                    rd = host_rays[f][1].to(dev, non_blocking=True)
                     rgb, disp, acc, _ = nb.render(H, W, K, chunk=args.chunk, rays=(ro, rd), near=NEAR, far=FAR,
                                                   **kw_test)
-                else:
-                    rgb, disp, acc = parallel.render_sharded(nb.render, H, W, K, ro, rd, chunk=args.chunk, near=NEAR,
-                                                             far=FAR, **kw_test)
+                else:       # each rank uploads its own slice of the frame's rays
+                    rgb, disp, acc = parallel.render_sharded(nb.render, H, W, K, host_rays[f][0], host_rays[f][1],
+                                                             upload_to=dev, chunk=args.chunk, near=NEAR, far=FAR,
+                                                             **kw_test)
                 if rank == 0:
                     host_out[f][:, 0:3].copy_(rgb, non_blocking=True)
                     host_out[f][:, 3].copy_(disp, non_blocking=True)
@@ -304,7 +305,7 @@ def main():
                        "parallelism": f"ray-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "working set per frame (2.6 GB raw/depth buffers) >> 126 MB L2, no flush needed",
                        "weights": "random init, numpy PCG64 seeds 0/1"},
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * n_rays * 12 * world,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * n_rays * 12 * world,   # summed over ranks
                     "d2h_bytes_per_step": n_rays * 20 * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,

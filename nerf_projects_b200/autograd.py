@@ -90,9 +90,12 @@ class RenderRaysFn(Function):
         rays_d = rays[:, 3:6]
         z_c = ops.coarse_z(rays, S, cfg["lindisp"], t_rand)
         # training: keep the layer inputs of each pass for the backward when they fit (else recompute there)
+        # (cfg["train"] is decided by the caller, where grad mode is visible: inside Function.forward grad mode is
+        #  always off and ctx.needs_input_grad is set even under torch.no_grad())
         n_cp = len(list(net_c.parameters()))
-        train_c = any(ctx.needs_input_grad[6:6 + n_cp])
-        train_f = any(ctx.needs_input_grad[6 + (n_cp if net_f is not None else 0):])
+        train = bool(cfg.get("train", False))
+        train_c = train and any(ctx.needs_input_grad[6:6 + n_cp])
+        train_f = train and any(ctx.needs_input_grad[6 + (n_cp if net_f is not None else 0):])
         ctx.acts_c = ctx.acts_f = None
         if train_c and mlp.can_save_forward(net_c, R * S):
             raw_c, ctx.acts_c = mlp.forward_save_bf16(net_c, R, S, rays, z_c)

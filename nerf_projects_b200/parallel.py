@@ -22,19 +22,26 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int, int]:
     return lo, hi, per
 
 
-def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, **kwargs):
+def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=None, **kwargs):
     """Ray-sharded render of one frame: each rank renders rays[lo:hi] with
     ``render_fn`` (= nerf_projects_b200.render), then one all_gather assembles
-    [rgb(3), disp, acc] for the full frame on every rank.  Returns
-    (rgb [N,3], disp [N], acc [N]) for the N input rays."""
+    [rgb(3), disp, acc] for the full frame on every rank.  With ``upload_to=device`` the rays
+    are (pinned) host tensors and each rank copies only its own slice to its GPU.  Returns (rgb [N,3], disp [N], acc [N]) for the N input rays."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = rays_o.shape[0]
     lo, hi, per = shard_bounds(n, world, rank)
-    dev = rays_o.device
+    if upload_to is None:
+        dev = rays_o.device
+        my_o, my_d = rays_o[lo:hi], rays_d[lo:hi]
+    else:
+        # host (pinned) rays: every rank uploads only ITS slice to its GPU
+        dev = torch.device(upload_to)
+        my_o = rays_o[lo:hi].to(dev, non_blocking=True)
+        my_d = rays_d[lo:hi].to(dev, non_blocking=True)
     tile = torch.zeros((per, 5), dtype=torch.float32, device=dev)
     if hi > lo:
-        rgb, disp, acc, _ = render_fn(H, W, K, rays=(rays_o[lo:hi], rays_d[lo:hi]), **kwargs)
+        rgb, disp, acc, _ = render_fn(H, W, K, rays=(my_o, my_d), **kwargs)
         tile[:hi - lo, 0:3] = rgb
         tile[:hi - lo, 3] = disp
         tile[:hi - lo, 4] = acc

@@ -214,6 +214,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     params = list(network_fn.parameters())
     if network_fine is not None:
         params += list(network_fine.parameters())
+    cfg["train"] = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     (rgb, disp, acc, depth, weights, raw, z_vals, rgb0, disp0, acc0, depth0, z_std, z_samples) = \
         AG.RenderRaysFn.apply(cfg, ray_batch, t_rand, u, noise_c, noise_f, *params)
     ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}

@@ -294,3 +294,17 @@ def test_train_step_with_perturb_and_noise_runs_and_is_finite():
         nb.set_precision("bf16")
     assert torch.isfinite(loss) and all(torch.isfinite(p.grad).all() for p in grad_vars if p.grad is not None)
     assert extras["raw"].shape == (24, 192, 4)
+
+
+def test_inference_render_does_not_take_the_training_save_path():
+    """Under torch.no_grad() the fused forward must be the plain kernel (no activation stores): every fused-MLP launch of a
+    render goes through the event-timed inference entry point (regression: ctx.needs_input_grad is set even under no_grad)."""
+    import nerf_projects_b200 as nb
+    from nerf_projects_b200 import ops
+    kw, kw_train, grad_vars, optim = build("render_c1")
+    K1, c2w = O.blender_camera(64, 64, 30.0)
+    with torch.no_grad():
+        ops.profile_mlp(True)
+        nb.render(64, 64, K1, chunk=1024, c2w=T(c2w).to(DEV), near=2., far=6., **kw)
+        timed = ops.profile_mlp(False)
+    assert len(timed) == 2 * 4, f"expected 8 inference MLP launches (4 chunks x coarse+fine), saw {len(timed)}"
