@@ -279,8 +279,9 @@ def main():
         def step_train():
             parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, H, W, K, b_o, b_d, target,
                                         chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
-        step_train()
-        tr_steps = 2
+        for _ in range(3):
+            step_train()
+        tr_steps = 5
         tr_ms = timed(step_train, tr_steps)
         train = {"value": n_batch * tr_steps / (tr_ms * 1e-3), "unit": "rays/s", "ms_per_step": tr_ms / tr_steps,
                  "config": f"{n_batch}-ray batch, 64+128, perturb=1, raw_noise_std=1, MSE(rgb)+MSE(rgb0), Adam; "
@@ -309,7 +310,7 @@ def main():
                     "d2h_bytes_per_step": n_rays * 20 * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_fwd_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_kernel<FWD>", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                          "frac_of_burst_peak": achieved / pk["burst"],
