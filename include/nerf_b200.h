@@ -208,6 +208,12 @@ int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float
 /* Same for MN-major operands (the wgrad form): C[128,N] = At^T Bt, At [K,128], Bt [K,N] row-major,
  * K multiple of 16 (<= 128), N multiple of 64 (<= 256), single CTA. */
 int nerfb_umma_selftest_mn(int N, int K, const float* At, const float* Bt, float* C, void* stream);
+/* Test hook (host only, no GPU): static schedule of the fused MLP kernel, which = 0 forward with view directions,
+ * 1 forward without, 2 data-gradient chain.  h_loads: 2 ints per load {blob offset, bytes per CTA}; h_ops: 5 ints per
+ * op {load, tile, A source chunk (4 = encoding buffer), flags (1 first, 2 last, 4 release slot, 8 release enc,
+ * 16 N=128), block length on the first op of a block}.  Arrays must hold 44 loads / 84 ops. */
+int nerfb_debug_schedule(int which, int* h_nloads, int* h_nops, int* h_nlayers, int* h_loads, int* h_ops,
+                         int* h_ring_slots);
 /* Probe (tools/probe_bulk.py): cycles per chunk of the 1-D bulk-copy path, per CTA, ring of `depth`. */
 int nerfb_bulk_probe(const void* src, int src_bytes, int nchunks, int chunk_bytes, int pieces, int depth,
                      int nblocks, long long* out_cycles, void* stream);

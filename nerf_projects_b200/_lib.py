@@ -51,6 +51,7 @@ _SIGS = {
     "nerfb_umma_selftest_mn": ([_i, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_bulk_probe": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "nerfb_contention_probe": ([_vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "nerfb_debug_schedule": ([_i] + [C.POINTER(_i)] * 6, _i),
     "nerfb_watchdog_record": ([], C.POINTER(C.c_ulonglong)),
     "nerfb_set_trace": ([_vp], _i),
     "nerfb_adam_step": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll),

@@ -1056,3 +1056,21 @@ extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, con
   a.d_raw = d_raw;
   return launch_mlp(MODE_BWD, a, true, stream);
 }
+
+/* Debug / test hook: the static schedule of a kernel mode (0 forward with view directions, 1 forward without,
+ * 2 data-gradient chain) as flat int arrays -- loads: {blob offset, bytes per CTA}; ops: {load, tile, asrc, flags,
+ * block length (non-zero on the first op of a block)}.  Host only; lets the CPU test-suite check the ring invariants. */
+extern "C" int nerfb_debug_schedule(int which, int* h_nloads, int* h_nops, int* h_nlayers, int* h_loads, int* h_ops,
+                                    int* h_ring_slots) {
+  NERFB_REQUIRE(which >= 0 && which <= 2 && h_nloads && h_nops && h_nlayers && h_loads && h_ops && h_ring_slots,
+                "nerfb_debug_schedule: bad arguments");
+  static Sched s;
+  if (which == 2) build_schedule_bwd(s); else build_schedule(which == 0, s);
+  *h_nloads = s.nloads; *h_nops = s.nops; *h_nlayers = s.nlayers; *h_ring_slots = kNS;
+  for (int i = 0; i < s.nloads; ++i) { h_loads[2 * i] = (int)s.loads[i].off; h_loads[2 * i + 1] = (int)s.loads[i].bytes; }
+  for (int i = 0; i < s.nops; ++i) {
+    h_ops[5 * i + 0] = s.ops[i].load; h_ops[5 * i + 1] = s.ops[i].tile & 0xF; h_ops[5 * i + 2] = s.ops[i].asrc;
+    h_ops[5 * i + 3] = s.ops[i].flags; h_ops[5 * i + 4] = s.ops[i].tile >> 4;
+  }
+  return NERFB_OK;
+}
