@@ -73,6 +73,17 @@ int nerfb_pack_rays(int n, const float* rays_o, const float* rays_d, const float
 int nerfb_coarse_z(int R, int S, const float* rays, int ray_width, int lindisp,
                    const float* t_rand, float* z, void* stream);
 
+/* Ray-batch producer of train() (ipynb:1167-1255: `use_batching` shuffled rays_rgb, or per-image
+ * get_rays + np.random.choice of pixel coordinates): rays of n SELECTED pixels generated from
+ * (pose, intrinsics, pixel) with get_rays' exact arithmetic, and their target colours gathered.
+ * sel[i] = image*H*W + row*W + col when img0 < 0, else the pixel id (row*W + col) inside image img0.
+ * poses: [n_images] blocks of pose_stride floats holding a row-major [3,4] (12) or [4,4] (16) c2w.
+ * images: [n_images,H,W,3] or NULL (then target is not written). */
+int nerfb_gather_ray_batch(int n, int H, int W, float fx, float fy, float cx, float cy,
+                           const float* poses, int pose_stride, int n_images, const float* images,
+                           const long long* sel, int img0, float* rays_o, float* rays_d, float* target,
+                           void* stream);
+
 /* ------------------------------------------------- positional encoding */
 
 /* Embedder.embed (embedder.py:36-80): out[i, col0 : col0+3+6L] =

@@ -8,6 +8,8 @@ and helper modules):
     raw2outputs, create_nerf, NeRF, Embedder, get_embedder, get_rays,
     get_rays_np, ndc_rays, sample_pdf, img2mse, mse2psnr, to8b
 
+plus RayBatcher, the device-side version of the ray-batch sampling block of train().
+
 All numerical work runs in hand-written CUDA (libnerf_b200.so, C ABI in
 include/nerf_b200.h).  There is no CPU fallback: importing works anywhere, but
 calling an op without the built library or without a CUDA device raises.
@@ -19,8 +21,9 @@ from .mlp import get_precision, set_precision  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .render import (batchify, batchify_rays, create_nerf, get_rays, get_rays_np, img2mse, mse2psnr,  # noqa: F401
                      ndc_rays, raw2outputs, render, render_path, render_rays, run_network, sample_pdf, to8b)
+from .data import RayBatcher, precrop_pixel_ids  # noqa: F401
 from . import ops  # noqa: F401
 
 __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network", "batchify", "raw2outputs",
            "create_nerf", "NeRF", "Embedder", "get_embedder", "get_rays", "get_rays_np", "ndc_rays", "sample_pdf",
-           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error"]
+           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids"]

@@ -28,6 +28,7 @@ _SIGS = {
     "nerfb_get_rays": ([_i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
     "nerfb_ndc_rays": ([_i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_pack_rays": ([_i, _vp, _vp, _vp, _i, _i, _i, _i, _d, _f, _f, _vp, _vp], _i),
+    "nerfb_gather_ray_batch": ([_i, _i, _i, _f, _f, _f, _f, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_coarse_z": ([_i, _i, _vp, _i, _i, _vp, _vp, _vp], _i),
     "nerfb_embed": ([_i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
     "nerfb_embed_samples": ([_i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),

@@ -26,6 +26,39 @@ __global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, floa
   }
 }
 
+
+// Ray-batch producer of train() (ipynb:1167-1255): rays of SELECTED pixels generated directly from
+// (pose, intrinsics, pixel id) -- same arithmetic as get_rays_kernel, so the values are bit-identical to
+// indexing the reference's per-image get_rays() output -- plus the gather of the target colours.
+// sel[i] = img * H*W + j*W + i (or pixel id only with a fixed image `img0`); poses: [N,3,4]; images [N,H,W,3].
+__global__ void gather_ray_batch_kernel(int n, int H, int W, float fx, float fy, float cx, float cy,
+                                        const float* __restrict__ poses, int pose_stride, const float* __restrict__ images,
+                                        const long long* __restrict__ sel, int img0, float* __restrict__ ro,
+                                        float* __restrict__ rd, float* __restrict__ target) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long hw = (long long)H * W;
+  long long s = __ldg(sel + t);
+  int img = img0;
+  if (img0 < 0) { img = (int)(s / hw); s -= (long long)img * hw; }
+  const int p = (int)s;
+  const float i = (float)(p % W), j = (float)(p / W);
+  const float dx = __fdiv_rn(__fsub_rn(i, cx), fx);
+  const float dy = -__fdiv_rn(__fsub_rn(j, cy), fy);
+  const float dz = -1.0f;
+  const float* c2w = poses + (size_t)img * pose_stride;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float r0 = __ldg(c2w + 4 * k + 0), r1 = __ldg(c2w + 4 * k + 1), r2 = __ldg(c2w + 4 * k + 2);
+    rd[3 * t + k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, r0), __fmul_rn(dy, r1)), __fmul_rn(dz, r2));
+    ro[3 * t + k] = __ldg(c2w + 4 * k + 3);
+  }
+  if (images != nullptr) {
+    const float* px = images + ((size_t)img * hw + p) * 3;
+    target[3 * t + 0] = __ldg(px + 0); target[3 * t + 1] = __ldg(px + 1); target[3 * t + 2] = __ldg(px + 2);
+  }
+}
+
 struct NdcConst {
   float sx, sy, near_f, two_near, neg_two_near;
 };
@@ -145,4 +178,16 @@ extern "C" int nerfb_coarse_z(int R, int S, const float* rays, int ray_width, in
   if (R == 0) return NERFB_OK;
   coarse_z_kernel<<<cdiv((long long)R * S, 256), 256, 0, as_stream(stream)>>>(R, S, rays, ray_width, lindisp, t_rand, z);
   return check_launch("coarse_z_kernel");
+}
+
+extern "C" int nerfb_gather_ray_batch(int n, int H, int W, float fx, float fy, float cx, float cy, const float* poses,
+                                      int pose_stride, int n_images, const float* images, const long long* sel, int img0,
+                                      float* rays_o, float* rays_d, float* target, void* stream) {
+  NERFB_REQUIRE(n >= 0 && H > 0 && W > 0 && poses && sel && rays_o && rays_d && pose_stride >= 12 && n_images > 0 &&
+                    img0 < n_images && (images == nullptr || target != nullptr),
+                "nerfb_gather_ray_batch: bad arguments");
+  if (n == 0) return NERFB_OK;
+  gather_ray_batch_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(n, H, W, fx, fy, cx, cy, poses, pose_stride, images,
+                                                                        sel, img0, rays_o, rays_d, target);
+  return check_launch("gather_ray_batch_kernel");
 }

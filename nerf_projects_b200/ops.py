@@ -69,6 +69,23 @@ def pack_rays(rays_o, rays_d, view_d, use_viewdirs, ndc, H, W, focal, near, far)
     return out
 
 
+def gather_ray_batch(H, W, fx, fy, cx, cy, poses, images, sel, img0=-1):
+    """rays_o, rays_d [n,3] (+ target [n,3] when images is given) of the selected pixels; see nerf_b200.h."""
+    L.require_cuda(poses, images, sel)
+    assert poses.dtype == torch.float32 and poses.is_contiguous() and sel.dtype == torch.int64 and sel.is_contiguous()
+    n = sel.numel()
+    stride = poses.shape[-2] * poses.shape[-1]
+    ro, rd = _empty((n, 3), poses), _empty((n, 3), poses)
+    tgt = _empty((n, 3), poses) if images is not None else None
+    if images is not None:
+        assert images.dtype == torch.float32 and images.is_contiguous() and images.shape[-1] == 3
+    L.check(L.load().nerfb_gather_ray_batch(n, int(H), int(W), float(fx), float(fy), float(cx), float(cy), L.ptr(poses),
+                                            int(stride), int(poses.shape[0]), L.ptr(images), L.ptr(sel), int(img0),
+                                            L.ptr(ro), L.ptr(rd), L.ptr(tgt), L.stream()), "nerfb_gather_ray_batch")
+    _count()
+    return ro, rd, tgt
+
+
 def coarse_z(rays, S, lindisp=False, t_rand=None):
     rays = L.f32c(rays)
     L.require_cuda(rays, t_rand)

@@ -249,3 +249,84 @@ def test_fused_adam_vs_torch_adam():
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
     o2 = torch.optim.Adam([p.detach().clone().requires_grad_(True) for p in p_gpu], lr=1e-3)
     o2.load_state_dict(sd)   # the reference's torch.optim.Adam accepts our checkpoints
+
+
+# ------------------------------------------------------------------ device-side ray-batch producer
+
+def _toy_dataset(n_img=5, H=20, W=28, seed=3):
+    gen = torch.Generator().manual_seed(seed)
+    images = torch.rand(n_img, H, W, 3, generator=gen)
+    poses = torch.stack([T(O.pose_spherical(40.0 * k, -30.0, 4.0))[:3, :4] for k in range(n_img)], 0).float()
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    return images, poses, H, W, K
+
+
+def test_gather_ray_batch_bit_exact_vs_per_image_get_rays():
+    """Rays produced for selected (image, pixel) pairs are bit-identical to indexing the reference's per-image
+    get_rays() output (oracle restatement, pinned to the reference by tests/golden/rays.npz), targets are the image pixels."""
+    from nerf_projects_b200 import ops
+    images, poses, H, W, K = _toy_dataset()
+    gen = torch.Generator().manual_seed(0)
+    n = 1000
+    img = torch.randint(0, images.shape[0], (n,), generator=gen)
+    pix = torch.randint(0, H * W, (n,), generator=gen)
+    sel = (img * H * W + pix).to(DEV)
+    ro, rd, tgt = ops.gather_ray_batch(H, W, K[0][0], K[1][1], K[0][2], K[1][2], poses.to(DEV), images.to(DEV), sel)
+    ref_o = torch.empty(n, 3); ref_d = torch.empty(n, 3)
+    for k in range(images.shape[0]):
+        o, d = O.get_rays(H, W, K, poses[k])
+        m = img == k
+        ref_o[m] = o.reshape(-1, 3)[pix[m]]
+        ref_d[m] = d.reshape(-1, 3)[pix[m]]
+    assert torch.equal(ro.cpu(), ref_o) and torch.equal(rd.cpu(), ref_d)
+    assert torch.equal(tgt.cpu(), images.reshape(-1, 3)[img * H * W + pix])
+    # fixed-image form
+    ro1, rd1, tgt1 = ops.gather_ray_batch(H, W, K[0][0], K[1][1], K[0][2], K[1][2], poses.to(DEV), images.to(DEV),
+                                          pix.to(DEV), img0=2)
+    o, d = O.get_rays(H, W, K, poses[2])
+    assert torch.equal(ro1.cpu(), o.reshape(-1, 3)[pix]) and torch.equal(rd1.cpu(), d.reshape(-1, 3)[pix])
+    assert torch.equal(tgt1.cpu(), images[2].reshape(-1, 3)[pix])
+
+
+def test_ray_batcher_modes():
+    """use_batching: every training pixel exactly once per epoch, then a reshuffle; per-image mode: one image per
+    batch, no repeated pixel, centre crop honoured while i < precrop_iters."""
+    import nerf_projects_b200 as nb
+    images, poses, H, W, K = _toy_dataset()
+    i_train = [0, 2, 3]
+    rb = nb.RayBatcher(images, poses, H, W, K, i_train=i_train, N_rand=112, use_batching=True, device=DEV, seed=1)
+    per_epoch = len(i_train) * H * W // 112
+    seen = []
+    for _ in range(per_epoch):
+        rays, tgt = rb.next_batch()
+        assert rays.shape == (2, 112, 3) and tgt.shape == (112, 3)
+        seen.append(tgt.cpu())
+    assert rb.epoch == 1
+    seen = torch.cat(seen, 0)
+    want = images[i_train].reshape(-1, 3)
+    # same multiset of target pixels
+    key = lambda t: (t.double() * torch.tensor([1.0, 3.0, 7.0], dtype=torch.float64)).sum(-1).sort()[0]
+    assert torch.equal(key(seen), key(want))
+    # rays belong to the pixel they are paired with: re-derive the ray of each target pixel
+    rays, tgt = rb.next_batch()
+    flat = images.reshape(-1, 3)
+    pos = (flat[None, :, :] == tgt.cpu()[:, None, :]).all(-1).float().argmax(1)
+    img, pix = pos // (H * W), pos % (H * W)
+    assert set(img.tolist()) <= set(i_train)
+    for k in set(img.tolist()):
+        o, d = O.get_rays(H, W, K, poses[k])
+        m = img == k
+        assert torch.equal(rays[1].cpu()[m], d.reshape(-1, 3)[pix[m]])
+    # per-image mode with centre crop
+    rb2 = nb.RayBatcher(images, poses, H, W, K, i_train=i_train, N_rand=40, use_batching=False, precrop_iters=3,
+                        precrop_frac=0.5, device=DEV, seed=2)
+    crop = set(nb.precrop_pixel_ids(H, W, 0.5).tolist())
+    for i in range(6):
+        rays, tgt = rb2.next_batch(i)
+        pos = (flat[None, :, :] == tgt.cpu()[:, None, :]).all(-1).float().argmax(1)
+        img, pix = pos // (H * W), pos % (H * W)
+        assert len(set(img.tolist())) == 1 and img[0].item() in i_train
+        assert len(set(pix.tolist())) == 40, "pixels must be drawn without replacement"
+        if i < 3:
+            assert set(pix.tolist()) <= crop
