@@ -14,10 +14,14 @@
 //     the same staged tiles (bias gradients = column sums of dY; alpha/rgb head gradients =
 //     d_raw-weighted column sums of h7 / hv) and, at the end of a work item, drain TMEM with
 //     red.global.add.f32 into the fp32 gradient tensors;
-//   * work = (layer job, range of stages): the virtual timeline sum_j bytes_j * nstages is cut
-//     into gridDim equal pieces, so the kernel is a split-K GEMM over all jobs at once and every
-//     byte of X / dY is read from HBM exactly once per job that needs it.
+//   * work = (layer job, range of stages): the SMs are dealt to the 12 jobs in proportion to the bytes
+//     a stage of each job moves (13 per plain layer, 8 per gamma(x) block, 15 for the views layer at 148
+//     SMs) and the CTAs of a job split its stages evenly, so the kernel is a split-K GEMM over all jobs
+//     at once with ONE work item -- one TMEM drain -- per CTA, and every byte of X / dY is read from HBM
+//     exactly once per job that needs it.  The drain uses 16-byte vector reductions where rows are
+//     aligned (the fixed cost of a launch fell from 0.33 ms to the value in profiles/README.md).
 // Bound: HBM (10.4 KB per sample against 1.19 MFLOP), see DESIGN.md.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc05.cuh"
 #include "mlp_layout.cuh"
@@ -40,6 +44,11 @@ static_assert(kWgSmemBytes <= 232448, "shared memory budget exceeded");
 static_assert(kStageStride % 1024 == 0, "stage buffers must keep the swizzle phase");
 
 enum { SIMT_NONE = 0, SIMT_ALPHA = 1, SIMT_RGB = 2 };
+
+// 16-byte vector reduction into global memory (one L2 atomic operation for four floats)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 struct WJob {
   uint32_t a_off;          // gradient panels inside a bwd tile (gstore)
@@ -64,6 +73,7 @@ struct WArgs {
   const uint8_t* gstore;
   const float* d_raw;      // [ntiles*128, 4], zero beyond the real rows
   long long nstages;       // 2 per 128-sample tile
+  int cta_begin[kMaxJobs + 1];   // CTAs [cta_begin[j], cta_begin[j+1]) split job j's stages evenly: ONE work item per CTA
   Watch watch;
 };
 
@@ -73,7 +83,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
   const uint32_t sbase = smem_u32(smem);
   __shared__ uint32_t tmem_slot;
   auto bar = [&](int i) -> uint32_t { return sbase + kWgSmBars + 8 * i; };
-  const int B_FULL = 0, B_EMPTY = kWgStages, B_ACC = 2 * kWgStages, B_FREE = 2 * kWgStages + 1;
+  const int B_FULL = 0, B_EMPTY = kWgStages, B_ACC = 2 * kWgStages;
 
   if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xB11, sbase, 0);
   if (tid == 0) {
@@ -82,7 +92,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
       mbar_init(bar(B_EMPTY + s), 1 + 4);     // tcgen05.commit + one arrive per SIMT warp
     }
     mbar_init(bar(B_ACC), 1);
-    mbar_init(bar(B_FREE), 4);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -94,107 +103,79 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  // ---- my slice of the virtual timeline (units: job weight x stages)
-  long long total = 0;
-  for (int j = 0; j < a.njobs; ++j) total += (long long)a.jobs[j].weight * a.nstages;
-  const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
-  // item iterator (identical in every role): job j, stages [s0, s1)
-  auto item = [&](int j, long long& s0, long long& s1) -> bool {
-    long long base = 0;
-    for (int q = 0; q < j; ++q) base += (long long)a.jobs[q].weight * a.nstages;
-    const long long w = a.jobs[j].weight;
-    const long long b0 = lo > base ? lo : base;
-    const long long e0 = hi < base + w * a.nstages ? hi : base + w * a.nstages;
-    if (e0 <= b0) return false;
-    s0 = (b0 - base + w - 1) / w;
-    s1 = (e0 - base + w - 1) / w;
-    return s1 > s0;
-  };
+  // ---- my work item: job jmine, stages [s0, s1) (the CTAs of a job split its stages evenly)
+  int jmine = 0;
+  while (jmine + 1 < a.njobs && (int)blockIdx.x >= a.cta_begin[jmine + 1]) ++jmine;
+  const int nsplit = a.cta_begin[jmine + 1] - a.cta_begin[jmine], isplit = (int)blockIdx.x - a.cta_begin[jmine];
+  const long long s0 = a.nstages * isplit / nsplit, s1 = a.nstages * (isplit + 1) / nsplit;
+  const bool has_work = s1 > s0;
+  const WJob& jb = a.jobs[jmine];
 
   if (warp == 0) {
     // ===================== loader
-    if (lane == 0) {
+    if (lane == 0 && has_work) {
       long long g = 0;
-      for (int j = 0; j < a.njobs; ++j) {
-        long long s0, s1;
-        if (!item(j, s0, s1)) continue;
-        const WJob& jb = a.jobs[j];
-        const int npan = jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + jb.x_panels;
-        for (long long s = s0; s < s1; ++s, ++g) {
-          const int slot = (int)(g % kWgStages);
-          if (g >= kWgStages) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((g / kWgStages) + 1) & 1), a.watch, 0x1100 + j);
-          const uint32_t dst = sbase + slot * kStageStride;
-          const uint32_t fb = bar(B_FULL + slot);
-          mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u);
-          const size_t tile = (size_t)(s >> 1), half = (size_t)(s & 1) * kHalfPanel;
-          const uint8_t* gt = a.gstore + tile * kBwdTileBytes + jb.a_off + half;
-          const uint8_t* ft = a.acts + tile * kFwdTileBytes + half;
-          int p = 0;
-          for (int i = 0; i < jb.a_panels; ++i, ++p) bulk_g2s(dst + p * kHalfPanel, gt + (size_t)i * kPanel, kHalfPanel, fb);
-          for (int grp = 0; grp < 2; ++grp)
-            for (int i = 0; i < jb.b_panels[grp]; ++i, ++p)
-              bulk_g2s(dst + p * kHalfPanel, ft + jb.b_off[grp] + (size_t)i * kPanel, kHalfPanel, fb);
-          for (int i = 0; i < jb.x_panels; ++i, ++p)
-            bulk_g2s(dst + p * kHalfPanel, ft + jb.x_off + (size_t)i * kPanel, kHalfPanel, fb);
-          bulk_g2s(dst + kStageDraw, a.d_raw + (size_t)s * kStageRows * 4, 1024, fb);
-        }
+      const int npan = jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + jb.x_panels;
+      for (long long s = s0; s < s1; ++s, ++g) {
+        const int slot = (int)(g % kWgStages);
+        if (g >= kWgStages) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((g / kWgStages) + 1) & 1), a.watch, 0x1100 + jmine);
+        const uint32_t dst = sbase + slot * kStageStride;
+        const uint32_t fb = bar(B_FULL + slot);
+        mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u);
+        const size_t tile = (size_t)(s >> 1), half = (size_t)(s & 1) * kHalfPanel;
+        const uint8_t* gt = a.gstore + tile * kBwdTileBytes + jb.a_off + half;
+        const uint8_t* ft = a.acts + tile * kFwdTileBytes + half;
+        int p = 0;
+        for (int i = 0; i < jb.a_panels; ++i, ++p) bulk_g2s(dst + p * kHalfPanel, gt + (size_t)i * kPanel, kHalfPanel, fb);
+        for (int grp = 0; grp < 2; ++grp)
+          for (int i = 0; i < jb.b_panels[grp]; ++i, ++p)
+            bulk_g2s(dst + p * kHalfPanel, ft + jb.b_off[grp] + (size_t)i * kPanel, kHalfPanel, fb);
+        for (int i = 0; i < jb.x_panels; ++i, ++p)
+          bulk_g2s(dst + p * kHalfPanel, ft + jb.x_off + (size_t)i * kPanel, kHalfPanel, fb);
+        bulk_g2s(dst + kStageDraw, a.d_raw + (size_t)s * kStageRows * 4, 1024, fb);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues)
-    long long g = 0;
-    int nitem = 0;
-    for (int j = 0; j < a.njobs; ++j) {
-      long long s0, s1;
-      if (!item(j, s0, s1)) continue;
-      const WJob& jb = a.jobs[j];
-      if (nitem > 0) {                       // accumulators of the previous item must have been drained
-        mbar_wait(bar(B_FREE), (uint32_t)((nitem - 1) & 1), a.watch, 0x1200 + j);
-        tc_fence_after();
-      }
+    // ===================== MMA issuer (one elected lane)
+    if (has_work && elect_one()) {
+      long long g = 0;
       const int nmh = jb.a_panels / 2;
       const uint32_t idesc0 = make_idesc_bf16_mn(128, 64 * jb.b_panels[0]);
       const uint32_t idesc1 = make_idesc_bf16_mn(128, jb.b_panels[1] ? 64 * jb.b_panels[1] : 64);
       for (long long s = s0; s < s1; ++s, ++g) {
         const int slot = (int)(g % kWgStages);
-        mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1300 + j);
+        mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1300 + jmine);
         tc_fence_after();
         const uint32_t st = sbase + slot * kStageStride;
-        if (elect_one()) {
-          for (int mh = 0; mh < nmh; ++mh) {
-            const uint64_t da = make_sdesc_sw128_mn(st + mh * 2 * kHalfPanel, kHalfPanel);
-            const uint64_t db0 = make_sdesc_sw128_mn(st + jb.a_panels * kHalfPanel, kHalfPanel);
-            const uint32_t acc0 = (s > s0) ? 1u : 0u;
+        for (int mh = 0; mh < nmh; ++mh) {
+          const uint64_t da = make_sdesc_sw128_mn(st + mh * 2 * kHalfPanel, kHalfPanel);
+          const uint64_t db0 = make_sdesc_sw128_mn(st + jb.a_panels * kHalfPanel, kHalfPanel);
+          const uint32_t acc0 = (s > s0) ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < kStageRows / 16; ++k)
+            umma_bf16<1>(tmem_base + mh * 256, da + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc0,
+                         (k > 0) ? 1u : acc0);
+          if (jb.b_panels[1]) {
+            const uint64_t db1 = make_sdesc_sw128_mn(st + (jb.a_panels + jb.b_panels[0]) * kHalfPanel, kHalfPanel);
+            const uint32_t d1 = tmem_base + mh * 256 + 64 * jb.b_panels[0];   // only used with one M half (views)
 #pragma unroll
             for (int k = 0; k < kStageRows / 16; ++k)
-              umma_bf16<1>(tmem_base + mh * 256, da + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc0,
-                           (k > 0) ? 1u : acc0);
-            if (jb.b_panels[1]) {
-              const uint64_t db1 = make_sdesc_sw128_mn(st + (jb.a_panels + jb.b_panels[0]) * kHalfPanel, kHalfPanel);
-              const uint32_t d1 = tmem_base + mh * 256 + 64 * jb.b_panels[0];   // only used with one M half (views)
-#pragma unroll
-              for (int k = 0; k < kStageRows / 16; ++k)
-                umma_bf16<1>(d1, da + (uint64_t)(k * 128), db1 + (uint64_t)(k * 128), idesc1, (k > 0) ? 1u : acc0);
-            }
+              umma_bf16<1>(d1, da + (uint64_t)(k * 128), db1 + (uint64_t)(k * 128), idesc1, (k > 0) ? 1u : acc0);
           }
-          umma_commit<1>(bar(B_EMPTY + slot));
-          if (s + 1 == s1) umma_commit<1>(bar(B_ACC));
         }
-        __syncwarp();
+        umma_commit<1>(bar(B_EMPTY + slot));
+        if (s + 1 == s1) umma_commit<1>(bar(B_ACC));
       }
-      ++nitem;
     }
+    __syncwarp();
   } else {
     // ===================== SIMT reductions + epilogue (warps 2..5, TMEM lane quarter = warp % 4)
     const int st_id = tid - 64;                 // 0..127
     const int q = warp & 3;
     const int row_in_half = 32 * q + lane;      // accumulator lane = output feature within the M half
     long long g = 0;
-    int nitem = 0;
-    for (int j = 0; j < a.njobs; ++j) {
-      long long s0, s1;
-      if (!item(j, s0, s1)) continue;
-      const WJob& jb = a.jobs[j];
+    if (has_work) {
+      const int j = jmine;
       // per-thread SIMT accumulators.  Mapping for 4-panel operands: 16-byte unit u = st_id & 7 (8 columns)
       // of panel (st_id >> 3) & 3, rows r = (st_id >> 5) mod 4; a warp reads 4 full 128-byte rows per LDS.128.
       float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias: 8 columns of dY
@@ -275,7 +256,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
           for (int k = 0; k < 3; ++k) atomicAdd(jb.head_b + k, hb[k]);
       }
       // ---- drain the accumulators: dW[out, col_off + c] += D[out, c]
-      mbar_wait(bar(B_ACC), (uint32_t)(nitem & 1), a.watch, 0x1500 + j);
+      mbar_wait(bar(B_ACC), 0u, a.watch, 0x1500 + j);
       tc_fence_after();
       const int nmh = jb.a_panels / 2;
       for (int mh = 0; mh < nmh; ++mh) {
@@ -284,23 +265,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
         for (int grp = 0; grp < 2; ++grp) {
           const int ncol_g = 64 * jb.b_panels[grp];
           float* dst = jb.dW + (size_t)out * jb.ld + jb.col_off[grp];
+          const bool vec = ((jb.ld | jb.col_off[grp]) & 3) == 0 && jb.ncols[grp] == ncol_g;   // 16-byte aligned rows
           for (int c0 = 0; c0 < ncol_g; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + mh * 256 + cbase + c0, v);
             tmem_ld_wait();
+            if (vec) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + i < jb.ncols[grp]) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; i += 4)
+                red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                           __uint_as_float(v[i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < jb.ncols[grp]) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+            }
           }
           cbase += ncol_g;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_FREE));
-      ++nitem;
     }
   }
+
 
   tc_fence_before();
   __syncthreads();
@@ -320,6 +306,11 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
   WArgs a{};
   int n = 0;
   auto G = [&](int i) { return h_grads[i]; };
+  // relative cost of one 64-sample stage of each job kind (bytes/1024 for the HBM-bound plain layers; the narrow
+  // gamma(x) jobs move 41 KB but pay the same CUDA-core bias reduction, so they weigh more than their bytes)
+  int narrow_w = 50, views_w = 9 * 8 + 1;   // (measured sweep: profiles/README.md)
+  if (const char* e = getenv("NERFB_WG_NARROW_W")) narrow_w = atoi(e);
+  if (const char* e = getenv("NERFB_WG_VIEWS_W")) views_w = atoi(e);
   auto plain = [&](uint32_t a_off, uint32_t b_off, float* dW, int ld, int col_off, float* dbias) {
     WJob j{};
     j.a_off = a_off; j.a_panels = 4;
@@ -335,7 +326,7 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
     j.b_off[0] = kFXg; j.b_panels[0] = 1;
     j.dW = dW; j.ld = ld; j.col_off[0] = 0; j.ncols[0] = 63;
     j.dbias = dbias;
-    j.weight = 5 * 8 + 1;
+    j.weight = narrow_w;
     return j;
   };
   const uint32_t dY = kGY, hL = kFH;
@@ -364,7 +355,7 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
     j.dbias = G(NERFB_P_VIEWS_B);
     j.simt = SIMT_RGB;
     j.head_w = G(NERFB_P_RGB_W); j.head_b = G(NERFB_P_RGB_B);
-    j.weight = 9 * 8 + 1;
+    j.weight = views_w;
     a.jobs[n++] = j;
   }
   a.njobs = n;
@@ -378,9 +369,32 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
     NERFB_CUDA(cudaFuncSetAttribute(nerf_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     attr_set = true;
   }
-  int grid = sm_count();
-  const long long units = (long long)a.njobs * a.nstages;
-  if (units < grid) grid = (int)units;
+  // deal the SMs to the jobs in proportion to their per-stage bytes (largest remainder), at least one each
+  const int grid = sm_count() >= a.njobs ? sm_count() : a.njobs;
+  {
+    int total_w = 0;
+    for (int j = 0; j < a.njobs; ++j) total_w += a.jobs[j].weight;
+    int cnt[kMaxJobs], used = 0;
+    double frac[kMaxJobs];
+    for (int j = 0; j < a.njobs; ++j) {
+      const double ideal = (double)grid * a.jobs[j].weight / total_w;
+      cnt[j] = (int)ideal < 1 ? 1 : (int)ideal;
+      frac[j] = ideal - cnt[j];
+      used += cnt[j];
+    }
+    while (used < grid) {
+      int best = 0;
+      for (int j = 1; j < a.njobs; ++j) if (frac[j] > frac[best]) best = j;
+      ++cnt[best]; frac[best] -= 1.0; ++used;
+    }
+    while (used > grid) {
+      int best = -1;
+      for (int j = 0; j < a.njobs; ++j) if (cnt[j] > 1 && (best < 0 || frac[j] < frac[best])) best = j;
+      --cnt[best]; frac[best] += 1.0; --used;
+    }
+    a.cta_begin[0] = 0;
+    for (int j = 0; j < a.njobs; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + cnt[j];
+  }
   nerf_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, as_stream(stream)>>>(a);
   return check_launch("nerf_wgrad_kernel");
 }
