@@ -141,7 +141,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 2048
+    n = 8192
     rate, dt, cores = cpu_reference_rate(n, args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": "rays/s (64+128 samples) render", "value": rate, "unit": "rays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
@@ -320,8 +320,8 @@ def main():
         if train is not None:
             line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
-            n = 2048
-            rate, dt, cores = cpu_reference_rate(n, 1, 1)
+            n = 8192
+            rate, dt, cores = cpu_reference_rate(n, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"{n}-ray subset of the same frame (64+128, viewdirs), oracle port on "
                                               f"torch CPU fp32 with {cores} threads, {dt:.1f} s"}
