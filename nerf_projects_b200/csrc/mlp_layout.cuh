@@ -15,10 +15,6 @@ constexpr int kChunkBytes = 16384;             // 128 rows x 64 bf16 (one K chun
 constexpr int kNS = NERFB_RING_SLOTS;          // weight ring slots of 16 KB per CTA (4 = one 256x256 layer)
 constexpr int kThreads = 384;                  // warps: 0 loader, 1 mma, 2 tmem, 3 relay, 4..11 epilogue
 constexpr int kEpiThreads = 256;
-#ifndef NERFB_LOAD_PIECES
-#define NERFB_LOAD_PIECES 4
-#endif
-constexpr int kLoadPieces = NERFB_LOAD_PIECES;   // bulk copies per weight chunk
 
 // packed weight blob: bf16 chunk images, then the fp32 parameter block
 constexpr int kChunkFull = 2 * kChunkBytes;    // N=256 chunk: two CTA halves
@@ -44,12 +40,7 @@ constexpr int kSmAct = 0;                      // 2 tiles x 4 chunks
 constexpr int kSmEnc = 2 * 4 * kChunkBytes;    // 131072: gamma(x) / gamma(d) operand chunk
 constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
 constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
-#ifdef NERFB_EXP_FAKEPAR          // timing experiment only: no parameter block in shared memory (results are garbage)
-constexpr int kSmSig = kSmParams;
-#else
-constexpr int kSmSig = kSmParams + kParamBytes;
-#endif
-constexpr int kSmSigUnused = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
+constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
 constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
 constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
 constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
@@ -74,7 +65,6 @@ constexpr int kGHv = 0;                               // d hv                2 p
 constexpr int kGFeat = 2 * kPanel;                    // d feature           4 panels
 constexpr int kGY = 6 * kPanel;                       // dY_l, l=0..7        4 panels each
 constexpr int kBwdTileBytes = kGY + 8 * 4 * kPanel;   // 38 panels = 608 KB
-constexpr int kMaskWords = 72;                        // per sample: ReLU masks, word l*8 + half*4 + batch; hv at 64..67
 constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7^T..L1^T(28)
 constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
 enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2 };

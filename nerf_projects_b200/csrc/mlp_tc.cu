@@ -1,4 +1,5 @@
-// Fused NeRF MLP forward on tcgen05 tensor cores (sm_100a).
+// Fused NeRF MLP on tcgen05 tensor cores (sm_100a): forward, forward-with-save (training) and the
+// data-gradient chain of the backward, one templated persistent kernel.
 //
 // Replaces run_network + NeRF.forward (ipynb:790-855, nerf.py:57-111) for all
 // R*S ray samples of a chunk: sample positions o + d*z, the sin/cos positional
@@ -6,8 +7,11 @@
 // feature / view-dependent layers and the rgb head run inside ONE persistent
 // kernel; activations live in shared memory (bf16) and TMEM (fp32
 // accumulators) and never touch HBM.  Output: raw[R*S, 4] = [rgb logits, sigma].
+// MODE_FWD_SAVE additionally bulk-stores every layer input for the weight-gradient
+// kernel (wgrad_tc.cu); MODE_BWD runs d_raw -> d_hv -> d_feature -> dY_7..dY_0 through
+// the transposed weights with the same machinery.
 //
-// Design (DESIGN.md section 4 has the full derivation):
+// Design (DESIGN.md section 4 has the full derivation and the measurements):
 //   * one 2-CTA cluster per SM pair, tcgen05.mma.cta_group::2 (UMMA M=256,
 //     N=256, K=16): each CTA owns 128 rows (samples) of A and HALF of the weight
 //     rows of B, so a whole 256x256 layer is 64 KB per CTA and stays resident
@@ -17,8 +21,11 @@
 //     tile B, the 8 epilogue warps drain tile A's accumulator from TMEM
 //     (bias, ReLU, bf16, 128B-swizzled store = next layer's A operand);
 //   * weights are pre-packed (nerfb_pack_weights) as the exact shared-memory
-//     images (K-major, SWIZZLE_128B) and streamed with 1-D bulk async copies
-//     (cp.async.bulk, TMA engine) signalled on mbarriers;
+//     images (K-major, SWIZZLE_128B) and streamed with tensor-map TMA copies
+//     (cp.async.bulk.tensor.2d, .cta_group::2) whose bytes complete on the
+//     LEADER CTA's mbarrier from both CTAs -- no relay between the CTAs;
+//   * the MMA issuer is one elected lane running a static schedule of BLOCKS
+//     (one tile's pass over one layer) with minimal work between MMA groups;
 //   * the density head is evaluated in fp32 from the un-rounded layer-7
 //     accumulators, the rgb head in fp32 from the fp32 view
 //     layer activations;
@@ -153,12 +160,8 @@ struct MlpArgs {
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
 };
 constexpr int kTraceLen = 4096;
-// training tile stores: bulk (TMA) copies out of the activation buffers (default), or 16-byte stores from the
-// epilogue registers (measured: forward+save 1.69 ms vs 1.02 ms, chain 2.09 vs 1.66 ms -- kept for reference only)
-#ifndef NERFB_BULK_SAVE
-#define NERFB_BULK_SAVE 1
-#endif
-constexpr bool kBulkSave = NERFB_BULK_SAVE != 0;
+// Training tile stores are bulk (TMA) copies out of the activation buffers.  Writing them with 16-byte stores from the
+// epilogue registers was measured and rejected (forward+save 1.69 ms vs 1.02 ms, chain 2.09 vs 1.66 ms; profiles/README.md).
 static long long* g_trace = nullptr;
 
 // ------------------------------------------------------------- encoding
@@ -214,11 +217,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   const int cluster_id = blockIdx.x >> 1;
   const uint32_t sbase = smem_u32(smem);
 
-#ifdef NERFB_EXP_FAKEPAR
-  float* s_par = reinterpret_cast<float*>(smem + kSmEnc);
-#else
   float* s_par = reinterpret_cast<float*>(smem + kSmParams);
-#endif
   float* s_sig = reinterpret_cast<float*>(smem + kSmSig);
   auto bar = [&](int i) -> uint32_t { return sbase + kSmBars + 8 * i; };
   const int B_FULL = 0, B_EMPTY = kNS, B_ACT = 2 * kNS, B_DONE = 2 * kNS + 2, B_ENC = 2 * kNS + 4;
@@ -259,9 +258,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   }
   {
     const float* gpar = reinterpret_cast<const float*>(a.packed + a.param_off);
-#ifndef NERFB_EXP_FAKEPAR
     for (int i = tid; i < kParamFloats; i += kThreads) s_par[i] = __ldg(gpar + i);
-#endif
   }
   if (warp == 2) {
     tmem_alloc<2>(sbase + kSmTmemSlot, 512);
@@ -400,11 +397,11 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     auto publish = [&](int t, bool signal, uint8_t* gdst, int npanels) {
       tc_fence_before();
       fence_proxy_async_smem();
-      if (kBulkSave && (SAVE || BWD) && et == 0) bulk_wait_read0();
+      if ((SAVE || BWD) && et == 0) bulk_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0) {
         if (signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
-        if (kBulkSave && (SAVE || BWD) && gdst != nullptr) {
+        if ((SAVE || BWD) && gdst != nullptr) {
           for (int pnl = 0; pnl < npanels; ++pnl)
             bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
           bulk_commit();
@@ -526,8 +523,6 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               const int col0 = 128 * hh + 32 * b;
 #ifndef NERFB_EXP_NOSTS
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
-              if (SAVE && !kBulkSave)     // training store straight from registers (same image as the smem operand)
-                store_row32(gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat) + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
 #else
               if (w[0] == 0x12345678u) store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
 #endif
@@ -657,7 +652,6 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               o[i] = pack_bf16x2(g0, g1) & bf16x2_nonzero_mask(mm[i]);
             }
             *reinterpret_cast<uint4*>(act_t + hh * kChunkBytes + off) = make_uint4(o[0], o[1], o[2], o[3]);
-            if (!kBulkSave) *reinterpret_cast<uint4*>(gtile[t] + kGHv + hh * kPanel + off) = make_uint4(o[0], o[1], o[2], o[3]);
           }
           publish(t, true, gtile[t] + kGHv, 2);
         }
@@ -721,8 +715,6 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               }
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
-              if (!kBulkSave)
-                store_row32(gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel) + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
             }
             if (et == 0) tr(2, 0x800 + j * 2 + t);
             uint8_t* gdst = gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);
