@@ -265,6 +265,11 @@ def _train_workspace(dev, nrows, need_acts=True):
     return ws
 
 
+def release_workspaces():
+    """Free the cached training tile stores (up to ~10 GB per device; they are re-created on demand)."""
+    _workspaces.clear()
+
+
 def supports_bf16_backward(net) -> bool:
     return bool(net.is_canonical() and net.use_viewdirs)
 

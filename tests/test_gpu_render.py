@@ -359,3 +359,25 @@ def test_full_size_frames_properties_and_oracle_spot_check(cfg):
     good = ((e_rgb <= 2e-2) & (e_acc <= 2e-2)).float().mean().item()
     print(f"{cfg}: {good:.4f} of 1024 spot-check rays within 2e-2 (max rgb err {e_rgb.max():.3e}, acc {e_acc.max():.3e})")
     assert good >= 0.9
+
+
+def test_render_path_matches_per_frame_render_and_reports_psnr(tmp_path):
+    """render_path (ipynb:650-758): frames copied to the host under the next frame's render must equal per-frame
+    render() calls; PSNR/MSE against given ground-truth images."""
+    import nerf_projects_b200 as nb
+    kw, _, _, _ = build("render_c1")
+    kw = dict(kw); kw.update(ndc=False, near=2., far=6.)
+    H = W = 40
+    K, _ = O.blender_camera(H, W, 0.0)
+    poses = [T(O.blender_camera(H, W, 25.0 * k)[1]).float().to(DEV) for k in range(4)]
+    with torch.no_grad():
+        frames = [nb.render(H, W, K, chunk=512, c2w=p[:3, :4], **kw) for p in poses]
+        gt = [f[0].cpu().numpy() * 0.9 for f in frames]
+        rgbs, disps, stats = nb.render_path(poses, (H, W, K[0][0]), K, 512, kw, gt_imgs=gt, savedir=str(tmp_path),
+                                            calculate_metrics=True, metrics_include_lpips=False)
+    assert rgbs.shape == (4, H, W, 3) and disps.shape == (4, H, W)
+    for k in range(4):
+        assert np.array_equal(rgbs[k], frames[k][0].cpu().numpy()) and np.array_equal(disps[k], frames[k][1].cpu().numpy())
+    want_mse = np.mean([np.mean((rgbs[k] - gt[k]) ** 2) for k in range(4)])
+    assert abs(stats["avg_mse"] - want_mse) < 1e-6 and stats["avg_psnr"] > 0
+    assert len(list(tmp_path.iterdir())) == 4
