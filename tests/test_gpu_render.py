@@ -381,3 +381,59 @@ def test_render_path_matches_per_frame_render_and_reports_psnr(tmp_path):
     want_mse = np.mean([np.mean((rgbs[k] - gt[k]) ** 2) for k in range(4)])
     assert abs(stats["avg_mse"] - want_mse) < 1e-6 and stats["avg_psnr"] > 0
     assert len(list(tmp_path.iterdir())) == 4
+
+
+@pytest.mark.parametrize("precision,tol_loss,tol_par", [("fp32", 2e-5, 2e-4), ("bf16", 2e-2, None)])
+def test_training_trajectory_vs_oracle(precision, tol_loss, tol_par):
+    """Four optimisation steps of train() (ipynb:1258-1282: render, MSE(rgb)+MSE(rgb0), backward, Adam, lr decay) on the
+    golden ray batch against the same loop run by the CPU oracle (torch autograd + torch.optim.Adam on the restated
+    render_rays).  fp32 mode: losses and parameters track tightly; bf16 mode (forward AND backward on the tensor cores):
+    losses within the render tolerance and the updates pointing the same way."""
+    import nerf_projects_b200 as nb
+    g = gold("train_grads")
+    kw, kw_train, grad_vars, optim = build("render_c1_sharp")
+    pc, pf = case_params("render_c1_sharp")
+    K1, _ = O.blender_camera(800, 800, 30.0)
+    ro, rd, target = T(g["rays_o"]), T(g["rays_d"]), T(g["target"])
+    # ---- oracle loop (CPU)
+    opc = {k: v.clone().requires_grad_(True) for k, v in O.to_torch(pc).items()}
+    opf = {k: v.clone().requires_grad_(True) for k, v in O.to_torch(pf).items()}
+    oopt = torch.optim.Adam(list(opc.values()) + list(opf.values()), lr=5e-4, betas=(0.9, 0.999))
+    rays_packed, _ = O.pack_rays(ro, rd, 2.0, 6.0, use_viewdirs=True)
+    ref_losses = []
+    for step in range(4):
+        out = O.render_rays(rays_packed, opc, opf, N_samples=64, N_importance=128, white_bkgd=True)
+        loss = O.img2mse(out["rgb_map"], target) + O.img2mse(out["rgb0"], target)
+        oopt.zero_grad(); loss.backward(); oopt.step()
+        for gparam in oopt.param_groups:
+            gparam["lr"] = 5e-4 * (0.1 ** ((step + 1) / (250 * 1000)))
+        ref_losses.append(float(loss))
+    # ---- ours
+    nb.set_precision(precision)
+    try:
+        start = [p.detach().clone() for p in grad_vars]
+        losses = []
+        for step in range(4):
+            rgb, disp, acc, extras = nb.render(800, 800, K1, chunk=32768, rays=(ro.to(DEV), rd.to(DEV)), near=2., far=6.,
+                                               retraw=True, **kw)
+            loss = nb.img2mse(rgb, target.to(DEV)) + nb.img2mse(extras["rgb0"], target.to(DEV))
+            optim.zero_grad(); loss.backward(); optim.step()
+            for gparam in optim.param_groups:
+                gparam["lr"] = 5e-4 * (0.1 ** ((step + 1) / (250 * 1000)))
+            losses.append(float(loss))
+    finally:
+        nb.set_precision("bf16")
+    print(f"{precision}: losses {losses} vs oracle {ref_losses}")
+    assert all(abs(a - b) <= tol_loss for a, b in zip(losses, ref_losses)), (losses, ref_losses)
+    names = [f"c.{n}" for n, _ in kw["network_fn"].named_parameters()] + [f"f.{n}" for n, _ in kw["network_fine"].named_parameters()]
+    oref = dict([(f"c.{k}", v) for k, v in opc.items()] + [(f"f.{k}", v) for k, v in opf.items()])
+    worst = 1.0
+    for name, p0, p in zip(names, start, grad_vars):
+        want = oref[name].detach()
+        if tol_par is not None:
+            assert (p.detach().cpu() - want).abs().max().item() <= tol_par, name
+        du, dr = (p.detach().cpu() - p0.cpu()).flatten().double(), (want - O.to_torch(pc if name[0] == "c" else pf)[name[2:]]).flatten().double()
+        if dr.norm() > 0:
+            worst = min(worst, float(torch.dot(du, dr) / (du.norm() * dr.norm() + 1e-30)))
+    print(f"{precision}: worst cosine between our 4-step parameter update and the oracle's: {worst:.4f}")
+    assert worst > (0.99 if precision == "fp32" else 0.85)
