@@ -36,6 +36,8 @@ inline int check_launch(const char* what) {
     }                                                                           \
   } while (0)
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

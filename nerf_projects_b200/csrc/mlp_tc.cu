@@ -969,6 +969,7 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
                                   const float* viewdirs, int use_viewdirs, int out_ch, const void* packed, float* raw,
                                   void* stream) {
   NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw, "nerfb_mlp_fwd_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(packed) && aligned16(raw), "nerfb_mlp_fwd_bf16: packed / raw must be 16-byte aligned");
   NERFB_REQUIRE(use_viewdirs || (out_ch >= 1 && out_ch <= 5), "nerfb_mlp_fwd_bf16: out_ch=%d unsupported", out_ch);
   NERFB_REQUIRE(pts || (rays && z && ray_width >= 8), "nerfb_mlp_fwd_bf16: need pts or rays+z");
   NERFB_REQUIRE(!use_viewdirs || viewdirs || (rays && ray_width >= 11),
@@ -992,6 +993,8 @@ extern "C" int nerfb_mlp_fwd_save_bf16(int R, int S, const float* rays, int ray_
                                        const float* pts, const float* viewdirs, const void* packed, float* raw,
                                        void* acts, void* stream) {
   NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw && acts, "nerfb_mlp_fwd_save_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(packed) && aligned16(raw) && aligned16(acts),
+                "nerfb_mlp_fwd_save_bf16: packed / raw / acts must be 16-byte aligned");
   NERFB_REQUIRE(pts || (rays && z && ray_width >= 8), "nerfb_mlp_fwd_save_bf16: need pts or rays+z");
   NERFB_REQUIRE(viewdirs || (rays && ray_width >= 11), "nerfb_mlp_fwd_save_bf16: view directions not provided");
   if (R == 0) return NERFB_OK;
@@ -1038,6 +1041,8 @@ extern "C" int nerfb_pack_weights_bwd(const float* const* h_params, void* packed
 extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* packed_bwd, const void* acts,
                                         void* gstore, void* stream) {
   NERFB_REQUIRE(nrows >= 0 && d_raw && packed_bwd && acts && gstore, "nerfb_mlp_bwd_chain_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(d_raw) && aligned16(packed_bwd) && aligned16(acts) && aligned16(gstore),
+                "nerfb_mlp_bwd_chain_bf16: all buffers must be 16-byte aligned");
   if (nrows == 0) return NERFB_OK;
   MlpArgs a{};
   a.nrows = nrows; a.S = 1; a.use_viewdirs = 1; a.out_ch = 4;

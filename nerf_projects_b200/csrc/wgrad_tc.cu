@@ -300,6 +300,10 @@ using namespace nerfb;
 extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore, const float* d_raw_padded,
                                     float* const* h_grads, void* stream) {
   NERFB_REQUIRE(nrows >= 0 && acts && gstore && d_raw_padded && h_grads, "nerfb_mlp_wgrad_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(acts) && aligned16(gstore) && aligned16(d_raw_padded),
+                "nerfb_mlp_wgrad_bf16: acts / gstore / d_raw_padded must be 16-byte aligned");
+  for (int i = 0; i < NERFB_P_OUTPUT_W; ++i)
+    NERFB_REQUIRE(h_grads[i] == nullptr || aligned16(h_grads[i]), "nerfb_mlp_wgrad_bf16: gradient tensor %d is not 16-byte aligned", i);
   for (int i = 0; i < NERFB_P_OUTPUT_W; ++i)
     NERFB_REQUIRE(h_grads[i], "nerfb_mlp_wgrad_bf16: gradient tensor %d missing", i);
   if (nrows == 0) return NERFB_OK;
