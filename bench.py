@@ -172,7 +172,7 @@ def main():
 
     import nerf_projects_b200 as nb
     from nerf_projects_b200 import ops, parallel
-    from oracle import nerf_oracle as O   # input generation (seeded params / camera) and the cpu_baseline leg only
+    from nerf_projects_b200 import synthetic as SY    # seeded weights / cameras (the product arm never imports oracle/)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,11 +186,11 @@ def main():
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         kw_train, kw_test, start, grad_vars, optim = nb.create_nerf(make_args(), device=dev)
-    kw_test["network_fn"].load_state_dict(O.to_torch(O.make_params(0, use_viewdirs=True, output_ch=5)))
-    kw_test["network_fine"].load_state_dict(O.to_torch(O.make_params(1, use_viewdirs=True, output_ch=5)))
+    kw_test["network_fn"].load_state_dict(SY.random_init_state_dict(0, use_viewdirs=True, output_ch=5))
+    kw_test["network_fine"].load_state_dict(SY.random_init_state_dict(1, use_viewdirs=True, output_ch=5))
     nb.set_precision("bf16")
-    K, _ = O.blender_camera(H, W, 30.0)
-    poses = [torch.from_numpy(O.blender_camera(H, W, 30.0 + 9.0 * i)[1]).to(dev) for i in range(max(world, 1) * 2)]
+    K, _ = SY.blender_shaped_camera(H, W, 30.0)
+    poses = [torch.from_numpy(SY.blender_shaped_camera(H, W, 30.0 + 9.0 * i)[1]).to(dev) for i in range(max(world, 1) * 2)]
     n_rays = H * W
 
     def frame_rays(i):

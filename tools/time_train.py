@@ -11,14 +11,14 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nerf_projects_b200 as nb  # noqa: E402
 from nerf_projects_b200 import mlp, ops  # noqa: E402
-from oracle import nerf_oracle as O  # noqa: E402  (seeded parameters only)
+from nerf_projects_b200 import synthetic as SY  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 S = 192
 dev = "cuda"
 net = nb.NeRF(8, 256, 63, 27, 5, [4], True).to(dev)
-net.load_state_dict(O.to_torch(O.make_params(1, use_viewdirs=True, output_ch=5)))
+net.load_state_dict(SY.random_init_state_dict(1, use_viewdirs=True, output_ch=5))
 gen = torch.Generator().manual_seed(0)
 rays = torch.cat([torch.randn(R, 3, generator=gen), torch.randn(R, 3, generator=gen), torch.full((R, 1), 2.0),
                   torch.full((R, 1), 6.0), torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=-1)],

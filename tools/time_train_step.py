@@ -2,11 +2,11 @@ import sys, torch, time
 sys.path.insert(0, "/root/repo")
 import nerf_projects_b200 as nb
 from nerf_projects_b200 import ops, parallel, mlp
-from oracle import nerf_oracle as O
+from nerf_projects_b200 import synthetic as SY
 import bench
 dev = torch.device("cuda")
 kw_train, kw_test, start, gv, optim = nb.create_nerf(bench.make_args(), device=dev)
-K, c2w = O.blender_camera(800, 800, 30.0)
+K, c2w = SY.blender_shaped_camera(800, 800, 30.0)
 ro, rd = nb.get_rays(800, 800, K, torch.from_numpy(c2w).cuda())
 ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
 kw = dict(kw_train); kw.update(ndc=False, lindisp=False, perturb=1.0, raw_noise_std=1.0)

@@ -4,10 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import nerf_projects_b200 as nb
 from nerf_projects_b200 import mlp, _lib
-from oracle import nerf_oracle as O
+from nerf_projects_b200 import synthetic as SY
 
 net = nb.NeRF(8, 256, 63, 27, 5, [4], True).cuda()
-net.load_state_dict(O.to_torch(O.make_params(0, use_viewdirs=True, output_ch=5)))
+net.load_state_dict(SY.random_init_state_dict(0, use_viewdirs=True, output_ch=5))
 R, S = 32768, 192
 g = torch.Generator().manual_seed(0)
 rays = torch.cat([torch.randn(R, 3, generator=g), torch.randn(R, 3, generator=g), torch.full((R, 1), 2.), torch.full((R, 1), 6.),
