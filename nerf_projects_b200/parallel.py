@@ -22,11 +22,12 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int, int]:
     return lo, hi, per
 
 
-def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=None, **kwargs):
+def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=None, return_packed=False, **kwargs):
     """Ray-sharded render of one frame: each rank renders rays[lo:hi] with
     ``render_fn`` (= nerf_projects_b200.render), then one all_gather assembles
     [rgb(3), disp, acc] for the full frame on every rank.  With ``upload_to=device`` the rays
-    are (pinned) host tensors and each rank copies only its own slice to its GPU.  Returns (rgb [N,3], disp [N], acc [N]) for the N input rays."""
+    are (pinned) host tensors and each rank copies only its own slice to its GPU.  Returns (rgb [N,3], disp [N], acc [N]) for the N input rays, or the
+    packed [N,5] tile tensor with ``return_packed=True``."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = rays_o.shape[0]
@@ -51,6 +52,8 @@ def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=Non
         full = torch.empty((world * per, 5), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(full, tile, group=group)
     full = full[:n]
+    if return_packed:          # [N,5] = rgb(3), disp, acc in one contiguous tensor (one D2H copy for the caller)
+        return full
     return full[:, 0:3], full[:, 3], full[:, 4]
 
 
