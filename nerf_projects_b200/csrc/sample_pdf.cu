@@ -188,7 +188,34 @@ hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, c
     for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     if (lane == 0) z_std[r] = (float)sqrt(var / N);
   }
-  // torch.sort(cat([z_vals, z_samples])): warp bitonic sort over P = pow2 >= S+N
+  // torch.sort(cat([z_vals, z_samples])) returns values only, so any correct sort is bit-identical.  When both lists
+  // are already non-decreasing (always for the coarse depths; for the new samples whenever u is sorted, i.e. the
+  // deterministic test-time case, up to last-ulp effects at bin edges) a merge-path merge does it in ~100
+  // instructions per lane; the check below keeps the general bitonic sort as the fallback, so the result never
+  // depends on that assumption.
+  bool sorted_in = true;
+  for (int i = lane; i < S + N; i += 32)
+    if (i != 0 && i != S && s_sort[i] < s_sort[i - 1]) sorted_in = false;
+  if (__all_sync(0xffffffffu, sorted_in)) {
+    const float* A = s_sort;            // S coarse depths
+    const float* B = s_sort + S;        // N new samples
+    const int T = S + N, per = (T + 31) / 32;
+    const int p0 = min(T, lane * per), p1 = min(T, p0 + per);
+    int lo = max(0, p0 - N), hi = min(p0, S);
+    while (lo < hi) {                   // number of A elements among the first p0 outputs (A first on ties)
+      const int mid = (lo + hi) >> 1;
+      if (A[mid] <= B[p0 - mid - 1]) lo = mid + 1; else hi = mid;
+    }
+    int i = lo, j = p0 - lo;
+    float* out = z_out + (size_t)r * T;
+    for (int p = p0; p < p1; ++p) {
+      const bool take_a = (i < S) && (j >= N || A[i] <= B[j]);
+      out[p] = take_a ? A[i] : B[j];
+      if (take_a) ++i; else ++j;
+    }
+    return;
+  }
+  // general case: warp bitonic sort over P = pow2 >= S+N
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = lane; t < P; t += 32) {
