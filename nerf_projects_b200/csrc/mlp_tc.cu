@@ -394,18 +394,31 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     // (optionally) tell the MMA issuer, and -- training modes -- bulk-store `npanels` panels of
     // act_t to `gdst`.  The pre-barrier wait covers the PREVIOUS bulk store (other tile, issued a
     // whole epilogue ago), so after the barrier every thread may overwrite that tile's buffer.
+    // Training stores are issued per 16 KB panel by the leader thread of the column half that wrote it (et == 0 for
+    // columns 0..127, et == 128 for 128..255): the FIRST panel of a half goes out mid-epilogue (store_first_panel),
+    // the second one here -- a 64 KB store issued only at the end finished reading shared memory too late and stalled
+    // the next publish on its wait_group.read.
+    const bool half_leader = (q == 0 && lane == 0);
     auto publish = [&](int t, bool signal, uint8_t* gdst, int npanels) {
       tc_fence_before();
       fence_proxy_async_smem();
-      if ((SAVE || BWD) && et == 0) bulk_wait_read0();
+      if ((SAVE || BWD) && half_leader) bulk_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et == 0) {
-        if (signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
-        if ((SAVE || BWD) && gdst != nullptr) {
-          for (int pnl = 0; pnl < npanels; ++pnl)
-            bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
-          bulk_commit();
-        }
+      if (et == 0 && signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
+      if ((SAVE || BWD) && half_leader && gdst != nullptr) {
+        const int pnl = (npanels == 4) ? 2 * hh + 1 : hh;          // 4 panels: my half's second; 2 panels: my chunk
+        bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
+        bulk_commit();
+      }
+    };
+    // first panel (columns 128*hh .. 128*hh+63) of a 4-panel tile: complete after the second 32-column batch of my half
+    auto store_first_panel = [&](int t, uint8_t* gdst) {
+      fence_proxy_async_smem();
+      if (hh == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+      else asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (half_leader) {
+        bulk_s2g(gdst + 2 * hh * kPanel, sbase + kSmAct + (t * 4 + 2 * hh) * kChunkBytes, kPanel);
+        bulk_commit();
       }
     };
     auto signal_ready = [&](int t) { publish(t, true, nullptr, 0); };
@@ -523,6 +536,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               const int col0 = 128 * hh + 32 * b;
 #ifndef NERFB_EXP_NOSTS
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+              if (SAVE && b == 1) store_first_panel(t, gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat));
 #else
               if (w[0] == 0x12345678u) store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
 #endif
@@ -715,6 +729,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               }
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+              if (b == 1) store_first_panel(t, gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel));
             }
             if (et == 0) tr(2, 0x800 + j * 2 + t);
             uint8_t* gdst = gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);
@@ -723,7 +738,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         }
       }
     }
-    if ((SAVE || BWD) && et == 0) bulk_wait0();
+    if ((SAVE || BWD) && half_leader) bulk_wait0();
   }
 
   // ---- teardown
