@@ -188,25 +188,25 @@ int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const flo
 /* ---- training: parameter gradients of the MLP on tensor cores (replaces the autograd graph of
  * NeRF.forward, nerf.py:57-111, under loss.backward(), ipynb:1274).  use_viewdirs networks only.
  * Three launches per network pass and ray chunk:
- *   1. nerfb_mlp_fwd_save_bf16: the fused forward again (activation recompute), which also
- *      bulk-stores every layer input as bf16 operand images into `acts`;
+ *   1. nerfb_mlp_fwd_save_bf16: the fused forward, which also bulk-stores every layer input as
+ *      bf16 operand images into `acts` and one ReLU sign bit per hidden unit into `masks`;
  *   2. nerfb_mlp_bwd_chain_bf16: data gradients d_raw -> d_hv -> d_feature -> dY_7..dY_0 through
- *      the transposed weights (nerfb_pack_weights_bwd), ReLU masks from `acts`, gradients
+ *      the transposed weights (nerfb_pack_weights_bwd), ReLU masks from `masks`, gradients
  *      bulk-stored into `gstore`;
  *   3. nerfb_mlp_wgrad_bf16: dW += dY^T X, db += colsum(dY) for all 12 Linear layers, fp32
  *      accumulation in TMEM, added (red.global.add.f32) into the caller's fp32 gradient tensors.
- * nerfb_train_store_bytes(nrows, 0|1): bytes of `acts` / `gstore` for nrows samples (whole
+ * nerfb_train_store_bytes(nrows, 0|1|2): bytes of `acts` / `gstore` / `masks` for nrows samples (whole
  * 512-row super-tiles).  d_raw: [nrows,4] = d loss / d raw.  d_raw_padded: the same buffer but
  * allocated (and zero beyond nrows) up to a multiple of 512 rows.  h_grads: host array of
  * NERFB_NUM_PARAMS device pointers (NERFB_P_* order, state_dict shapes), accumulated into. */
 size_t nerfb_train_store_bytes(long long nrows, int which);
 int nerfb_mlp_fwd_save_bf16(int R, int S, const float* rays, int ray_width, const float* z,
                             const float* pts, const float* viewdirs, const void* packed, float* raw,
-                            void* acts, void* stream);
+                            void* acts, void* masks, void* stream);
 size_t nerfb_packed_weights_bwd_bytes(void);
 int nerfb_pack_weights_bwd(const float* const* h_params, void* packed_bwd, void* stream);
 int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* packed_bwd,
-                             const void* acts, void* gstore, void* stream);
+                             const void* masks, void* gstore, void* stream);
 int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore,
                          const float* d_raw_padded, float* const* h_grads, void* stream);
 /* Self-test of the tcgen05 building blocks (smem descriptors, 128B swizzle,

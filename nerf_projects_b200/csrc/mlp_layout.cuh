@@ -65,6 +65,12 @@ constexpr int kGHv = 0;                               // d hv                2 p
 constexpr int kGFeat = 2 * kPanel;                    // d feature           4 panels
 constexpr int kGY = 6 * kPanel;                       // dY_l, l=0..7        4 panels each
 constexpr int kBwdTileBytes = kGY + 8 * 4 * kPanel;   // 38 panels = 608 KB
+// ReLU masks for the data-gradient chain: one SIGN bit per unit (1 = pre-activation negative = inactive), collected by
+// the forward-with-save epilogue; per 128-sample tile [9 layers: h0..h7, hv][128 rows][2 column halves][4 words], word b of
+// a half covers its columns 32b..32b+31 with column j at bit 31 - j.  36 KB per tile (the bf16 activations are 640 KB).
+constexpr int kMaskLayers = 9;
+constexpr int kMaskRowBytes = 32;
+constexpr int kMaskTileBytes = kMaskLayers * 128 * kMaskRowBytes;
 constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7^T..L1^T(28)
 constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
 enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2 };

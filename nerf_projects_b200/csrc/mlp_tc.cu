@@ -154,7 +154,8 @@ struct MlpArgs {
   int nst, nclusters;
   Watch watch;
   long long* trace;   // debug timeline (nerfb_set_trace), 3 regions of kTraceLen entries
-  uint8_t* acts;      // MODE_FWD_SAVE (out) / MODE_BWD (in, ReLU masks): [ntiles][kFwdTileBytes]
+  uint8_t* acts;      // MODE_FWD_SAVE (out): [ntiles][kFwdTileBytes]
+  uint8_t* masks;     // MODE_FWD_SAVE (out) / MODE_BWD (in): ReLU sign bits, [ntiles][kMaskTileBytes]
   uint8_t* gstore;    // MODE_BWD: [ntiles][kBwdTileBytes]
   const float* d_raw; // MODE_BWD: [nrows,4]
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
@@ -402,7 +403,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     auto publish = [&](int t, bool signal, uint8_t* gdst, int npanels) {
       tc_fence_before();
       fence_proxy_async_smem();
-      if ((SAVE || BWD) && half_leader) bulk_wait_read0();
+      // what must have left shared memory before the barrier: the OTHER tile's stores (its buffer is overwritten by
+      // the next epilogue).  This tile's own first-panel store, issued half an epilogue ago, may still be in flight.
+      if ((SAVE || BWD) && half_leader) { if (gdst != nullptr && npanels == 4) bulk_wait_read1(); else bulk_wait_read0(); }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0 && signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
       if ((SAVE || BWD) && half_leader && gdst != nullptr) {
@@ -471,9 +474,12 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       grow[1] = grow[0] + 2 * kTileRows;
       // global 128-row tile index of (tile t, this CTA) and its training store
       uint8_t* gtile[2] = {nullptr, nullptr};
+      uint8_t* mtile[2] = {nullptr, nullptr};
       if (SAVE) {
         gtile[0] = a.acts + (size_t)(st * 4 + rank) * kFwdTileBytes;
         gtile[1] = a.acts + (size_t)(st * 4 + 2 + rank) * kFwdTileBytes;
+        mtile[0] = a.masks + (size_t)(st * 4 + rank) * kMaskTileBytes;
+        mtile[1] = a.masks + (size_t)(st * 4 + 2 + rank) * kMaskTileBytes;
       }
       for (int t = 0; t < 2; ++t) {       // layer-0 operands
         enc_wait();
@@ -493,6 +499,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             const float* hw = s_par + kOffHeadW + 128 * hh;
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
             float sig = 0.f;
+            uint32_t sbits[4] = {0u, 0u, 0u, 0u};     // MODE_FWD_SAVE: sign bits of my 4 x 32 pre-activations
             // software pipeline: the TMEM load of batch b+1 is in flight while batch b is processed
             uint32_t v[2][32];
 #ifndef NERFB_EXP_NOTMEM
@@ -516,6 +523,12 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 x[4 * j4 + 1] = __uint_as_float(vv[4 * j4 + 1]) + bb.y;
                 x[4 * j4 + 2] = __uint_as_float(vv[4 * j4 + 2]) + bb.z;
                 x[4 * j4 + 3] = __uint_as_float(vv[4 * j4 + 3]) + bb.w;
+              }
+              if (SAVE && l < 8) {                    // one funnel shift per unit: column j ends at bit 31 - j
+                uint32_t m = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m = __funnelshift_l(__float_as_uint(x[j]), m, 1);
+                sbits[b] = m;
               }
               if (l == 7) {
 #pragma unroll
@@ -542,6 +555,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
 #endif
             }
             if (l == 7) s_sig[(t * 2 + hh) * 128 + row] = sig;
+            if (SAVE && l < 8)
+              *reinterpret_cast<uint4*>(mtile[t] + ((size_t)l * 128 + row) * kMaskRowBytes + 16 * hh) =
+                  make_uint4(sbits[0], sbits[1], sbits[2], sbits[3]);
           } else if (l == 7) {
             // ---- no view directions: output_linear (out_ch x 256) in fp32 from layer-7 accumulators
             float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -572,6 +588,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             // ---- l == 9: view layer epilogue + rgb head -> raw (one warp quarter per 32 rows)
             if (hh == 0) {
               float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+              uint32_t sbits[4] = {0u, 0u, 0u, 0u};
               const float* bias = s_par + kOffBiasViews;
               const float* rw = s_par + kOffRgbW;
 #pragma unroll 1
@@ -580,14 +597,18 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 tmem_ld32(taddr + 32 * b, v);
                 tmem_ld_wait();
                 float xs[32];
+                uint32_t m = 0u;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  const float x = fmaxf(__uint_as_float(v[j]) + bias[32 * b + j], 0.f);
+                  const float pre = __uint_as_float(v[j]) + bias[32 * b + j];
+                  if (SAVE) m = __funnelshift_l(__float_as_uint(pre), m, 1);
+                  const float x = fmaxf(pre, 0.f);
                   xs[j] = x;
                   c0 = fmaf(x, rw[32 * b + j], c0);
                   c1 = fmaf(x, rw[128 + 32 * b + j], c1);
                   c2 = fmaf(x, rw[256 + 32 * b + j], c2);
                 }
+                if (SAVE) sbits[b] = m;
                 if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients
                   uint32_t w[16];
 #pragma unroll
@@ -596,6 +617,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                   store_row32(gtile[t] + kFHv + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
                 }
               }
+              if (SAVE)
+                *reinterpret_cast<uint4*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes) =
+                    make_uint4(sbits[0], sbits[1], sbits[2], sbits[3]);
               if (grow[t] < a.nrows) {
                 const float sigma = s_sig[(t * 2 + 0) * 128 + row] + s_sig[(t * 2 + 1) * 128 + row] + s_par[kOffHeadB];
                 *reinterpret_cast<float4*>(a.raw + grow[t] * 4) =
@@ -618,9 +642,10 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     }
     } else {
       // ================= MODE_BWD: data-gradient chain  d_raw -> d_hv -> d_feature -> dY_7 .. dY_0
-      // Layer j of the schedule multiplies by a transposed weight matrix; its epilogue applies the
-      // ReLU mask of the layer it lands on (read from the forward tile store), writes the bf16
-      // gradient as the next A operand and bulk-stores it for the weight-gradient kernel.
+      // Layer j of the schedule multiplies by a transposed weight matrix; its epilogue applies the ReLU
+      // mask of the layer it lands on (sign bits collected by the forward-with-save pass: 16 bytes per
+      // thread and tile-layer, expanded with prmt), writes the bf16 gradient as the next A operand and
+      // bulk-stores it for the weight-gradient kernel.
       const float* w_rgb = s_par + kOffRgbW;
       const float* w_alpha = s_par + kOffHeadW;
       for (int it = 0; it < niter; ++it) {
@@ -628,69 +653,49 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         long long grow[2];
         grow[0] = st * kSuperRows + rank * kTileRows + row;
         grow[1] = grow[0] + 2 * kTileRows;
-        const uint8_t* ftile[2];
+        const uint8_t* mtile[2];
         uint8_t* gtile[2];
         for (int t = 0; t < 2; ++t) {
           const size_t T = (size_t)(st * 4 + 2 * t + rank);
-          ftile[t] = a.acts + T * kFwdTileBytes;
+          mtile[t] = a.masks + T * kMaskTileBytes;
           gtile[t] = a.gstore + T * kBwdTileBytes;
         }
         float dsig[2];
-        if (et == 0) {
-          bulk_prefetch_l2(ftile[0] + kFH + 7 * 4 * kPanel, 4 * kPanel);
-          bulk_prefetch_l2(ftile[1] + kFH + 7 * 4 * kPanel, 4 * kPanel);
-          if (it + 1 < niter) {      // hv tiles of the next super-tile of this cluster
-            const size_t Tn = (size_t)((st + a.nclusters) * 4 + rank);
-            bulk_prefetch_l2(a.acts + Tn * kFwdTileBytes + kFHv, 2 * kPanel);
-            bulk_prefetch_l2(a.acts + (Tn + 2) * kFwdTileBytes + kFHv, 2 * kPanel);
-          }
-        }
         for (int t = 0; t < 2; ++t) {
           // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
           float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
           if (grow[t] < a.nrows) dr = __ldg(reinterpret_cast<const float4*>(a.d_raw) + grow[t]);
           dsig[t] = dr.w;
+          // hv sign bits: 4 words for columns 0..127; my chunk uses words 2*hh and 2*hh+1
+          const uint2 mhv = __ldg(reinterpret_cast<const uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
           uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
-          const uint8_t* hvp = ftile[t] + kFHv + hh * kPanel;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t off = sw128_offset(row, u);
-            const uint4 m = __ldg(reinterpret_cast<const uint4*>(hvp + off));
-            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
-            uint32_t o[4];
+          for (int half = 0; half < 2; ++half) {          // 32 columns at a time
+            uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = 64 * hh + 8 * u + 2 * i;
+            for (int i = 0; i < 16; ++i) {
+              const int c = 64 * hh + 32 * half + 2 * i;
               const float g0 = fmaf(dr.z, w_rgb[256 + c], fmaf(dr.y, w_rgb[128 + c], dr.x * w_rgb[c]));
               const float g1 = fmaf(dr.z, w_rgb[257 + c], fmaf(dr.y, w_rgb[129 + c], dr.x * w_rgb[c + 1]));
-              o[i] = pack_bf16x2(g0, g1) & bf16x2_nonzero_mask(mm[i]);
+              w[i] = pack_bf16x2(g0, g1);
             }
-            *reinterpret_cast<uint4*>(act_t + hh * kChunkBytes + off) = make_uint4(o[0], o[1], o[2], o[3]);
+            apply_sign_mask32(w, half == 0 ? mhv.x : mhv.y);
+            store_row32(act_t + hh * kChunkBytes, row, 4 * half, w);
           }
           publish(t, true, gtile[t] + kGHv, 2);
         }
         for (int j = 0; j < sc.nlayers; ++j) {
-          // masks come from h_m (bf16, post-ReLU) of the layer the gradient lands on
-          const int m = 8 - j;                       // j=1 -> h7 ... j=8 -> h0 ; j=0: feature (no ReLU)
+          const int m = 8 - j;                       // mask layer: j=1 -> h7 ... j=8 -> h0 ; j=0: feature (no ReLU)
           for (int t = 0; t < 2; ++t) {
-            const uint8_t* hsrc = ftile[t] + kFH + (m < 0 ? 0 : m) * 4 * kPanel;
             const int colbase = 128 * hh;
-            uint4 hm[2][4];
-            auto load_mask = [&](int b, uint4 (&dst)[4]) {
-              const int col0 = colbase + 32 * b;
-              const uint8_t* pp = hsrc + (col0 >> 6) * kPanel;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dst[i] = __ldg(reinterpret_cast<const uint4*>(pp + sw128_offset(row, ((col0 & 63) >> 3) + i)));
-            };
 #ifdef NERFB_EXP_NOMASK
             const bool use_mask = false;
 #else
             const bool use_mask = j > 0;
 #endif
-            if (use_mask) { load_mask(0, hm[0]); load_mask(1, hm[1]); }
-            // pull the NEXT layer's mask tile (64 KB) of this tile into L2 a whole layer ahead
-            if (et == 0 && j + 1 < sc.nlayers) bulk_prefetch_l2(ftile[t] + kFH + (m - 1) * 4 * kPanel, 4 * kPanel);
+            uint4 mw = make_uint4(0u, 0u, 0u, 0u);   // requested before the wait on the MMA: 16 bytes per thread
+            if (use_mask)
+              mw = __ldg(reinterpret_cast<const uint4*>(mtile[t] + ((size_t)m * 128 + row) * kMaskRowBytes + 16 * hh));
             mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
             done_cnt[t]++;
             if (et == 0) tr(2, 0x700 + j * 2 + t);
@@ -698,6 +703,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             const uint32_t taddr = tmem_base + lane_addr + t * 256;
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
             const float ds = dsig[t];
+            const uint32_t mwv[4] = {mw.x, mw.y, mw.z, mw.w};
             uint32_t v[2][32];
             tmem_ld32(taddr + colbase, v[0]);
 #pragma unroll
@@ -716,17 +722,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1]));
               }
-              if (use_mask) {
-                const uint4 (&mk)[4] = hm[b & 1];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  w[4 * i + 0] &= bf16x2_nonzero_mask(mk[i].x);
-                  w[4 * i + 1] &= bf16x2_nonzero_mask(mk[i].y);
-                  w[4 * i + 2] &= bf16x2_nonzero_mask(mk[i].z);
-                  w[4 * i + 3] &= bf16x2_nonzero_mask(mk[i].w);
-                }
-                if (b < 2) load_mask(b + 2, hm[b & 1]);
-              }
+              if (use_mask) apply_sign_mask32(w, mwv[b]);
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
               if (b == 1) store_first_panel(t, gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel));
@@ -1001,15 +997,15 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
 
 extern "C" size_t nerfb_train_store_bytes(long long nrows, int which) {
   const long long ntiles = 4 * ((nrows + kSuperRows - 1) / kSuperRows);
-  return (size_t)ntiles * (size_t)(which == 0 ? kFwdTileBytes : kBwdTileBytes);
+  return (size_t)ntiles * (size_t)(which == 0 ? kFwdTileBytes : (which == 1 ? kBwdTileBytes : kMaskTileBytes));
 }
 
 extern "C" int nerfb_mlp_fwd_save_bf16(int R, int S, const float* rays, int ray_width, const float* z,
                                        const float* pts, const float* viewdirs, const void* packed, float* raw,
-                                       void* acts, void* stream) {
-  NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw && acts, "nerfb_mlp_fwd_save_bf16: bad arguments");
-  NERFB_REQUIRE(aligned16(packed) && aligned16(raw) && aligned16(acts),
-                "nerfb_mlp_fwd_save_bf16: packed / raw / acts must be 16-byte aligned");
+                                       void* acts, void* masks, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw && acts && masks, "nerfb_mlp_fwd_save_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(packed) && aligned16(raw) && aligned16(acts) && aligned16(masks),
+                "nerfb_mlp_fwd_save_bf16: packed / raw / acts / masks must be 16-byte aligned");
   NERFB_REQUIRE(pts || (rays && z && ray_width >= 8), "nerfb_mlp_fwd_save_bf16: need pts or rays+z");
   NERFB_REQUIRE(viewdirs || (rays && ray_width >= 11), "nerfb_mlp_fwd_save_bf16: view directions not provided");
   if (R == 0) return NERFB_OK;
@@ -1019,6 +1015,7 @@ extern "C" int nerfb_mlp_fwd_save_bf16(int R, int S, const float* rays, int ray_
   a.packed = (const uint8_t*)packed; a.raw = raw; a.out_ch = 4;
   a.param_off = kChunkAreaVD;
   a.acts = (uint8_t*)acts;
+  a.masks = (uint8_t*)masks;
   return launch_mlp(MODE_FWD_SAVE, a, true, stream);
 }
 
@@ -1053,17 +1050,17 @@ extern "C" int nerfb_pack_weights_bwd(const float* const* h_params, void* packed
   return check_launch("pack_weights_bwd_kernel");
 }
 
-extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* packed_bwd, const void* acts,
+extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* packed_bwd, const void* masks,
                                         void* gstore, void* stream) {
-  NERFB_REQUIRE(nrows >= 0 && d_raw && packed_bwd && acts && gstore, "nerfb_mlp_bwd_chain_bf16: bad arguments");
-  NERFB_REQUIRE(aligned16(d_raw) && aligned16(packed_bwd) && aligned16(acts) && aligned16(gstore),
+  NERFB_REQUIRE(nrows >= 0 && d_raw && packed_bwd && masks && gstore, "nerfb_mlp_bwd_chain_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(d_raw) && aligned16(packed_bwd) && aligned16(masks) && aligned16(gstore),
                 "nerfb_mlp_bwd_chain_bf16: all buffers must be 16-byte aligned");
   if (nrows == 0) return NERFB_OK;
   MlpArgs a{};
   a.nrows = nrows; a.S = 1; a.use_viewdirs = 1; a.out_ch = 4;
   a.packed = (const uint8_t*)packed_bwd;
   a.param_off = kChunkAreaBwd;
-  a.acts = (uint8_t*)acts;
+  a.masks = (uint8_t*)masks;
   a.gstore = (uint8_t*)gstore;
   a.d_raw = d_raw;
   return launch_mlp(MODE_BWD, a, true, stream);

@@ -155,6 +155,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk groups of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // bulk prefetch of a global range into L2 (no destination; fire and forget)
@@ -366,6 +367,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// 32 sign bits (column j of a 32-column batch at bit 31 - j) -> zero the bf16 halves of w[16] whose sign bit is set.
+// prmt's sign-replicate mode turns the top bit of a selected byte into 0x00 / 0xFF, so after shifting the wanted bit to a
+// byte's msb one prmt builds the AND mask of a packed pair: 7 shifts + 16 prmt + 16 lop3 per 32 columns.
+__device__ __forceinline__ void apply_sign_mask32(uint32_t (&w)[16], uint32_t m) {
+  uint32_t ms[9];
+#pragma unroll
+  for (int s = 0; s < 9; ++s) ms[s] = m << s;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int j = 2 * i, s = j & 7, a = j >> 3;                 // column j sits at the msb of byte 3-a of (m << s)
+    const uint32_t sel = (uint32_t)((8 | (3 - a)) * 0x11) | ((uint32_t)((8 | (7 - a)) * 0x11) << 8);
+    uint32_t neg;                                               // 0xFFFF per half whose unit was inactive
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(neg) : "r"(ms[s]), "r"(ms[s + 1]), "r"(sel));
+    w[i] &= ~neg;
+  }
 }
 
 // per bf16 half: 0xFFFF where the half is non-zero (ReLU mask from a stored post-ReLU activation pair)

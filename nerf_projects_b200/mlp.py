@@ -253,14 +253,15 @@ def _param_ptrs(named):
 
 
 def _train_workspace(dev, nrows, need_acts=True):
-    """(acts, gstore) tile stores for up to nrows samples, cached per device (grown on demand)."""
-    need = (ops.train_store_bytes(nrows, 0) if need_acts else 0, ops.train_store_bytes(nrows, 1))
+    """(acts, gstore, masks) tile stores for up to nrows samples, cached per device (grown on demand)."""
+    need = (ops.train_store_bytes(nrows, 0) if need_acts else 0, ops.train_store_bytes(nrows, 1),
+            ops.train_store_bytes(nrows, 2) if need_acts else 0)
     ws = _workspaces.get(dev)
-    if ws is None or ws[0].numel() < need[0] or ws[1].numel() < need[1]:
-        sizes = (max(need[0], ws[0].numel() if ws else 0), max(need[1], ws[1].numel() if ws else 0))
+    if ws is None or any(w.numel() < n for w, n in zip(ws, need)):
+        sizes = tuple(max(n, ws[i].numel() if ws else 0) for i, n in enumerate(need))
         ws = None
         _workspaces.pop(dev, None)
-        ws = (torch.empty(sizes[0], dtype=torch.uint8, device=dev), torch.empty(sizes[1], dtype=torch.uint8, device=dev))
+        ws = tuple(torch.empty(n, dtype=torch.uint8, device=dev) for n in sizes)
         _workspaces[dev] = ws
     return ws
 
@@ -287,7 +288,7 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
     packed, packed_bwd = packed_weights(net), packed_weights_bwd(net)
     nchunk = max(1, -(-(R * S) // TRAIN_ROWS_PER_CHUNK))       # even split: no tiny tail chunk
     step = -(-R // nchunk)
-    acts, gstore = _train_workspace(dev, min(R, step) * S)
+    acts, gstore, masks = _train_workspace(dev, min(R, step) * S)
     d_raw = L.f32c(d_raw).view(-1, 4)
     for r0 in range(0, R, step):
         r1 = min(R, r0 + step)
@@ -297,8 +298,8 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
         d_pad[:n].copy_(d_raw[r0 * S:r1 * S])
         raw_tmp = torch.empty((n, 4), dtype=torch.float32, device=dev)
         ops.mlp_fwd_save_bf16(r1 - r0, S, _slice_rows(rays, r0, r1), _slice_rows(z, r0, r1),
-                              _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), packed, raw_tmp, acts)
-        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore)
+                              _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), packed, raw_tmp, acts, masks)
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore)
         ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs)
     return grads
 
@@ -314,24 +315,27 @@ def can_save_forward(net, nrows: int) -> bool:
 
 
 def forward_save_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
-    """Fused forward that also stores every layer input (bf16 operand images) -> (raw, acts)."""
+    """Fused forward that also stores every layer input (bf16 operand images) and the ReLU sign bits
+    -> (raw, (acts, masks))."""
     dev = net.pts_linears[0].weight.device
     n = R * S
     raw = torch.empty((n, 4), dtype=torch.float32, device=dev)
     acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device=dev)
-    ops.mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed_weights(net), raw, acts)
-    return raw, acts
+    masks = torch.empty(ops.train_store_bytes(n, 2), dtype=torch.uint8, device=dev)
+    ops.mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed_weights(net), raw, acts, masks)
+    return raw, (acts, masks)
 
 
-def backward_from_saved(net, nrows: int, acts, d_raw) -> Dict[str, torch.Tensor]:
-    """Parameter gradients from the activations a forward_save_bf16 pass stored (no recompute)."""
+def backward_from_saved(net, nrows: int, saved, d_raw) -> Dict[str, torch.Tensor]:
+    """Parameter gradients from what a forward_save_bf16 pass stored (no recompute)."""
+    acts, masks = saved
     dev = acts.device
     grads = {n: torch.zeros_like(p) for n, p in net.named_parameters()}
     npad = (nrows + 511) // 512 * 512
     d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
     d_pad[:nrows].copy_(L.f32c(d_raw).view(-1, 4))
-    _, gstore = _train_workspace(dev, nrows, need_acts=False)
-    ops.mlp_bwd_chain_bf16(nrows, d_pad, packed_weights_bwd(net), acts, gstore)
+    _, gstore, _ = _train_workspace(dev, nrows, need_acts=False)
+    ops.mlp_bwd_chain_bf16(nrows, d_pad, packed_weights_bwd(net), masks, gstore)
     ops.mlp_wgrad_bf16(nrows, acts, gstore, d_pad, _param_ptrs(grads))
     return grads
 

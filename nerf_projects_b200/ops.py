@@ -289,16 +289,16 @@ def pack_weights_bwd(param_ptrs: Sequence[Optional[int]], packed_bwd: torch.Tens
     _count()
 
 
-def mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed, raw, acts):
+def mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed, raw, acts, masks):
     L.check(L.load().nerfb_mlp_fwd_save_bf16(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
                                              L.ptr(z), L.ptr(pts), L.ptr(viewdirs), L.ptr(packed), L.ptr(raw),
-                                             L.ptr(acts), L.stream()), "nerfb_mlp_fwd_save_bf16")
+                                             L.ptr(acts), L.ptr(masks), L.stream()), "nerfb_mlp_fwd_save_bf16")
     _count()
     return raw
 
 
-def mlp_bwd_chain_bf16(nrows, d_raw, packed_bwd, acts, gstore):
-    L.check(L.load().nerfb_mlp_bwd_chain_bf16(int(nrows), L.ptr(d_raw), L.ptr(packed_bwd), L.ptr(acts),
+def mlp_bwd_chain_bf16(nrows, d_raw, packed_bwd, masks, gstore):
+    L.check(L.load().nerfb_mlp_bwd_chain_bf16(int(nrows), L.ptr(d_raw), L.ptr(packed_bwd), L.ptr(masks),
                                               L.ptr(gstore), L.stream()), "nerfb_mlp_bwd_chain_bf16")
     _count()
 

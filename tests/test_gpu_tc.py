@@ -206,8 +206,9 @@ def test_tc_backward_stages_vs_oracle(R, S):
         packed, packed_bwd = mlp.packed_weights(net), mlp.packed_weights_bwd(net)
         acts = torch.zeros(ops.train_store_bytes(n, 0), dtype=torch.uint8, device=DEV)
         gstore = torch.zeros(ops.train_store_bytes(n, 1), dtype=torch.uint8, device=DEV)
+        masks = torch.zeros(ops.train_store_bytes(n, 2), dtype=torch.uint8, device=DEV)
         raw = torch.empty(n, 4, device=DEV)
-        ops.mlp_fwd_save_bf16(R, S, rays.to(DEV), z.to(DEV), None, None, packed, raw, acts)
+        ops.mlp_fwd_save_bf16(R, S, rays.to(DEV), z.to(DEV), None, None, packed, raw, acts, masks)
         raw_plain = mlp.forward_bf16(net, R, S, rays.to(DEV), z.to(DEV))
         torch.cuda.synchronize()
         assert torch.equal(raw, raw_plain), "forward-with-save changed the forward result"
@@ -232,7 +233,7 @@ def test_tc_backward_stages_vs_oracle(R, S):
         npad = (n + 511) // 512 * 512
         d_pad = torch.zeros(npad, 4, device=DEV)
         d_pad[:n] = d_raw.to(DEV)
-        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore)
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore)
         torch.cuda.synchronize()
 
         def bwd_panels(off, npan):

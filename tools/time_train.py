@@ -31,15 +31,16 @@ d_pad[:n] = torch.randn(n, 4, generator=gen).to(dev)
 packed, packed_bwd = mlp.packed_weights(net), mlp.packed_weights_bwd(net)
 acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device=dev)
 gstore = torch.empty(ops.train_store_bytes(n, 1), dtype=torch.uint8, device=dev)
+masks = torch.empty(ops.train_store_bytes(n, 2), dtype=torch.uint8, device=dev)
 raw = torch.empty(n, 4, device=dev)
 grads = {k: torch.zeros_like(p) for k, p in net.named_parameters()}
 gptrs = mlp._param_ptrs(grads)
 
 legs = {
     "fwd": (lambda: ops._mlp_fwd_bf16(R, S, rays, z, None, None, True, 5, packed, raw), 1186816, 20),
-    "fwd_save": (lambda: ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts), 1186816, 5 * 1024 + 20),
-    "bwd_chain": (lambda: ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore), 2 * 557696,
-                  (4 * 8 + 2) * 128 + 38 * 128 + 16),
+    "fwd_save": (lambda: ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts, masks), 1186816, 5 * 1024 + 20),
+    "bwd_chain": (lambda: ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore), 2 * 557696,
+                  9 * 32 + 38 * 128 + 16),
     "wgrad": (lambda: ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs), 1186816, 10.4 * 1024),
 }
 for name, (fn, flop, bytes_per_row) in legs.items():

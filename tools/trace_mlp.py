@@ -21,6 +21,7 @@ if MODE != "fwd":
     rays, z = rays[:R].contiguous(), z[:R].contiguous()
     acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device="cuda")
     gstore = torch.empty(ops.train_store_bytes(n, 1), dtype=torch.uint8, device="cuda")
+    masks = torch.empty(ops.train_store_bytes(n, 2), dtype=torch.uint8, device="cuda")
     raw = torch.empty(n, 4, device="cuda")
     d_pad = torch.randn((n + 511) // 512 * 512, 4, device="cuda")
     packed, packed_bwd = mlp.packed_weights(net), mlp.packed_weights_bwd(net)
@@ -28,11 +29,11 @@ def run():
     if MODE == "fwd":
         mlp.forward_bf16(net, R, S, rays, z)
     elif MODE == "save":
-        ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts)
+        ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts, masks)
     else:
-        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, acts, gstore)
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore)
 if MODE == "chain":
-    ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts)
+    ops.mlp_fwd_save_bf16(R, S, rays, z, None, None, packed, raw, acts, masks)
 for _ in range(2):
     run()
 torch.cuda.synchronize()
