@@ -524,11 +524,15 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 x[4 * j4 + 2] = __uint_as_float(vv[4 * j4 + 2]) + bb.z;
                 x[4 * j4 + 3] = __uint_as_float(vv[4 * j4 + 3]) + bb.w;
               }
-              if (SAVE && l < 8) {                    // one funnel shift per unit: column j ends at bit 31 - j
-                uint32_t m = 0u;
+              if (SAVE && l < 8) {
+                // one funnel shift per unit (column j ends at bit 31 - j), as four independent 8-bit chains so the
+                // shifts do not serialise on one register
+                uint32_t m4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m = __funnelshift_l(__float_as_uint(x[j]), m, 1);
-                sbits[b] = m;
+                for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) m4[k] = __funnelshift_l(__float_as_uint(x[8 * k + jj]), m4[k], 1);
+                sbits[b] = (m4[0] << 24) | (m4[1] << 16) | (m4[2] << 8) | m4[3];
               }
               if (l == 7) {
 #pragma unroll
