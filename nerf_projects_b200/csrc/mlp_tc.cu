@@ -31,6 +31,7 @@
 //     layer activations;
 //   * every barrier wait is bounded by a watchdog (tc05.cuh).
 #include <cstdlib>
+#include <mutex>
 #include <cuda.h>
 #include "common.cuh"
 #include "tc05.cuh"
@@ -904,15 +905,17 @@ extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs
 // Tensor maps over a packed weight blob viewed as [rows][128 B] uint8 (images are pre-swizzled, so SWIZZLE_NONE):
 // box = 128 rows (one 16 KB chunk half) or 64 rows (views layer).  Cached per blob address.
 struct BlobMaps { const void* ptr; size_t bytes; CUtensorMap tm128, tm64; };
-static int get_blob_maps(const void* blob, size_t bytes, const BlobMaps** out) {
+static int get_blob_maps(const void* blob, size_t bytes, BlobMaps* out) {   // returns a COPY (the cache may evict)
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
   static BlobMaps cache[8];
   static int ncache = 0, victim = 0;
+  static std::mutex mu;                       // the cache is shared by all host threads / streams
+  std::lock_guard<std::mutex> lock(mu);
   for (int i = 0; i < ncache; ++i)
-    if (cache[i].ptr == blob && cache[i].bytes == bytes) { *out = &cache[i]; return NERFB_OK; }
+    if (cache[i].ptr == blob && cache[i].bytes == bytes) { *out = cache[i]; return NERFB_OK; }
   if (!encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -936,13 +939,15 @@ static int get_blob_maps(const void* blob, size_t bytes, const BlobMaps** out) {
   if (ncache < 8) slot = ncache++;
   else { slot = victim; victim = (victim + 1) % 8; }
   cache[slot] = m;
-  *out = &cache[slot];
+  *out = m;
   return NERFB_OK;
 }
 
 static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   static Sched sched_vd, sched_novd, sched_bwd;
   static bool init = false;
+  static std::mutex mu;
+  std::unique_lock<std::mutex> lock(mu);
   if (!init) {
     build_schedule(true, sched_vd);
     build_schedule(false, sched_novd);
@@ -952,6 +957,7 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     init = true;
   }
+  lock.unlock();
   a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
   a.nclusters = sm_count() / 2;
   if (const char* e = getenv("NERFB_MAX_CLUSTERS")) {      // experiments only (contention studies)
@@ -966,9 +972,10 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
-  const BlobMaps* maps = nullptr;
+  BlobMaps maps_v{};
+  const BlobMaps* maps = &maps_v;
   const size_t blob_bytes = (size_t)a.param_off + kParamBytes;
-  if (int rc = get_blob_maps(a.packed, blob_bytes, &maps)) return rc;
+  if (int rc = get_blob_maps(a.packed, blob_bytes, &maps_v)) return rc;
   if (mode == MODE_FWD) {
     NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
     return check_launch("nerf_mlp_kernel<FWD>");
