@@ -590,16 +590,18 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                                                 xch[((t * 2 + 1) * 128 + row) * 8 + k] + s_par[kOffHeadB + k];
             }
           } else {
-            // ---- l == 9: view layer epilogue + rgb head -> raw (one warp quarter per 32 rows)
-            if (hh == 0) {
+            // ---- l == 9: view layer epilogue + rgb head -> raw.  Both column halves work: thread (row, hh) takes
+            // view-layer columns 64*hh .. 64*hh+63; the hh == 1 partial rgb sums cross over through a scratch area
+            // (the unused output_linear rows of the parameter block) and hh == 0 writes the sample's raw[4].
+            {
               float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-              uint32_t sbits[4] = {0u, 0u, 0u, 0u};
-              const float* bias = s_par + kOffBiasViews;
-              const float* rw = s_par + kOffRgbW;
+              uint32_t sbits[2] = {0u, 0u};
+              const float* bias = s_par + kOffBiasViews + 64 * hh;
+              const float* rw = s_par + kOffRgbW + 64 * hh;
 #pragma unroll 1
-              for (int b = 0; b < 4; ++b) {
+              for (int b = 0; b < 2; ++b) {
                 uint32_t v[32];
-                tmem_ld32(taddr + 32 * b, v);
+                tmem_ld32(taddr + 64 * hh + 32 * b, v);
                 tmem_ld_wait();
                 float xs[32];
                 uint32_t m = 0u;
@@ -613,22 +615,25 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                   c1 = fmaf(x, rw[128 + 32 * b + j], c1);
                   c2 = fmaf(x, rw[256 + 32 * b + j], c2);
                 }
-                if (SAVE) sbits[b] = m;
-                if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients
+                if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients, and its sign bits
+                  sbits[b] = m;
                   uint32_t w[16];
 #pragma unroll
                   for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(xs[2 * i], xs[2 * i + 1]);
-                  const int col0 = 32 * b;
-                  store_row32(gtile[t] + kFHv + (col0 >> 6) * kPanel, row, (col0 & 63) >> 3, w);
+                  store_row32(gtile[t] + kFHv + hh * kPanel, row, 4 * b, w);
                 }
               }
               if (SAVE)
-                *reinterpret_cast<uint4*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes) =
-                    make_uint4(sbits[0], sbits[1], sbits[2], sbits[3]);
-              if (grow[t] < a.nrows) {
+                *reinterpret_cast<uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes + 8 * hh) =
+                    make_uint2(sbits[0], sbits[1]);
+              float* xch = s_par + kOffHeadW + 256 + (t * 128 + row) * 3;
+              if (hh == 1) { xch[0] = c0; xch[1] = c1; xch[2] = c2; }
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (hh == 0 && grow[t] < a.nrows) {
                 const float sigma = s_sig[(t * 2 + 0) * 128 + row] + s_sig[(t * 2 + 1) * 128 + row] + s_par[kOffHeadB];
                 *reinterpret_cast<float4*>(a.raw + grow[t] * 4) =
-                    make_float4(c0 + s_par[kOffRgbB], c1 + s_par[kOffRgbB + 1], c2 + s_par[kOffRgbB + 2], sigma);
+                    make_float4(c0 + xch[0] + s_par[kOffRgbB], c1 + xch[1] + s_par[kOffRgbB + 1],
+                                c2 + xch[2] + s_par[kOffRgbB + 2], sigma);
               }
             }
           }
