@@ -98,12 +98,13 @@ static void build_schedule(bool vd, Sched& s) {
     for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0));
     add_op(g2, 1, 4, f | F_LAST | F_REL_SLOT | F_REL_ENC);
   };
-  {  // layer 0: K = 64 (gamma(x)), one chunk used by both tiles
+  {  // layer 0: K = 64 (gamma(x), written by the epilogue warps into chunk 0 of the tile's own activation buffer),
+     // one weight chunk used by both tiles
     const uint8_t g0 = add_load(0, false);
     block(s.nops, 1);
-    add_op(g0, 0, 4, F_FIRST | F_LAST | F_REL_ENC);
+    add_op(g0, 0, 0, F_FIRST | F_LAST);
     block(s.nops, 1);
-    add_op(g0, 1, 4, F_FIRST | F_LAST | F_REL_ENC | F_REL_SLOT);
+    add_op(g0, 1, 0, F_FIRST | F_LAST | F_REL_SLOT);
   }
   for (int l = 1; l <= 4; ++l) plain(1 + 4 * (l - 1), false);
   with_enc(17, 18, false);          // layer 5: [gamma(x) | h4]
@@ -450,6 +451,17 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       }
     };
     // gsave != nullptr (MODE_FWD_SAVE): also write my half row of the panel image to global
+    // gamma(x) of tile t for LAYER 0 goes into chunk 0 of the tile's own activation buffer (free at that time), so
+    // it can be produced right after the tile's last epilogue of the previous super-tile, under the other tile's
+    // tail, instead of serialising both tiles through the shared enc buffer at the start of an iteration
+    auto write_first_layer_x = [&](int t, long long grow, uint8_t* gsave) {
+      float p[3];
+      load_point(grow, p);
+      uint32_t w[16];
+      if (hh == 0) encode_cols<10, 0>(p, w); else encode_cols<10, 1>(p, w);
+      store_row32(smem + kSmAct + t * 4 * kChunkBytes, row, 4 * hh, w);
+      if (SAVE && gsave != nullptr) store_row32(gsave, row, 4 * hh, w);
+    };
     auto write_enc_x = [&](long long grow, uint8_t* gsave) {
       float p[3];
       load_point(grow, p);
@@ -468,6 +480,14 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     };
 
     if constexpr (!BWD) {
+    if (niter > 0) {      // layer-0 operands of the first super-tile
+      const long long st0 = cluster_id;
+      for (int t = 0; t < 2; ++t) {
+        const long long g0 = st0 * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
+        write_first_layer_x(t, g0, SAVE ? a.acts + (size_t)(st0 * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
+        signal_ready(t);
+      }
+    }
     for (int it = 0; it < niter; ++it) {
       const long long st = cluster_id + (long long)it * a.nclusters;
       long long grow[2];
@@ -481,11 +501,6 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         gtile[1] = a.acts + (size_t)(st * 4 + 2 + rank) * kFwdTileBytes;
         mtile[0] = a.masks + (size_t)(st * 4 + rank) * kMaskTileBytes;
         mtile[1] = a.masks + (size_t)(st * 4 + 2 + rank) * kMaskTileBytes;
-      }
-      for (int t = 0; t < 2; ++t) {       // layer-0 operands
-        enc_wait();
-        write_enc_x(grow[t], SAVE ? gtile[t] + kFXg : nullptr);
-        signal_ready(t);
       }
       for (int l = 0; l < sc.nlayers; ++l) {
         for (int t = 0; t < 2; ++t) {
@@ -606,14 +621,24 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 float xs[32];
                 uint32_t m = 0u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float pre = __uint_as_float(v[j]) + bias[32 * b + j];
-                  if (SAVE) m = __funnelshift_l(__float_as_uint(pre), m, 1);
-                  const float x = fmaxf(pre, 0.f);
-                  xs[j] = x;
-                  c0 = fmaf(x, rw[32 * b + j], c0);
-                  c1 = fmaf(x, rw[128 + 32 * b + j], c1);
-                  c2 = fmaf(x, rw[256 + 32 * b + j], c2);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 bb = *reinterpret_cast<const float4*>(bias + 32 * b + 4 * j4);
+                  const float4 r0 = *reinterpret_cast<const float4*>(rw + 32 * b + 4 * j4);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rw + 128 + 32 * b + 4 * j4);
+                  const float4 r2 = *reinterpret_cast<const float4*>(rw + 256 + 32 * b + 4 * j4);
+                  const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, q0[4] = {r0.x, r0.y, r0.z, r0.w};
+                  const float q1[4] = {r1.x, r1.y, r1.z, r1.w}, q2[4] = {r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * j4 + jj;
+                    const float pre = __uint_as_float(v[j]) + bv[jj];
+                    if (SAVE) m = __funnelshift_l(__float_as_uint(pre), m, 1);
+                    const float x = fmaxf(pre, 0.f);
+                    xs[j] = x;
+                    c0 = fmaf(x, q0[jj], c0);
+                    c1 = fmaf(x, q1[jj], c1);
+                    c2 = fmaf(x, q2[jj], c2);
+                  }
                 }
                 if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients, and its sign bits
                   sbits[b] = m;
@@ -646,6 +671,16 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             uint8_t* gdst = nullptr;
             if (SAVE) gdst = gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat);
             publish(t, true, gdst, 4);
+          } else if (it + 1 < niter) {
+            // last layer of this tile: its buffers are free -> layer-0 operand of the NEXT super-tile right away
+            if (SAVE) {           // ... once the bulk store of `feature` has left the buffer
+              if (half_leader) bulk_wait_read0();
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const long long stn = st + a.nclusters;
+            write_first_layer_x(t, stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row,
+                                SAVE ? a.acts + (size_t)(stn * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
+            signal_ready(t);
           } else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
         }
       }
