@@ -169,16 +169,34 @@ static long long* g_trace = nullptr;
 
 // ------------------------------------------------------------- encoding
 // value of column c of gamma(p) (embedder.py:54-65): [p | sin f0 p | cos f0 p | sin f1 p | ...]
-// p*2^k is reduced to revolutions with a two-term 1/2pi so the MUFU argument is
-// accurate to ~1e-7 even at 2^9 * |p| ~ 3000 rad.
+// A thread produces 32 consecutive columns (HH = 0: columns 0..31, octaves 0..4; HH = 1: columns 32..63, octaves
+// 4..9).  Per dimension ONE accurate sin/cos at the thread's first octave -- p*2^k0 reduced to revolutions with a
+// two-term 1/2pi, MUFU on the reduced argument (~1e-7 even at 2^9*|p| ~ 3000 rad) -- and the higher octaves by the
+// double-angle recurrence (s' = 2sc, c' = 1 - 2s^2): at most 5 doublings, error <= ~3e-6, far below the bf16
+// rounding (4e-3) of the operand it feeds.  (The fp32 validation mode uses embed.cu, not this.)
 template <int L, int HH>
 __device__ __forceinline__ void encode_cols(const float (&p)[3], uint32_t (&packed)[16]) {
   constexpr float kInv2PiHi = 0.15915494f, kInv2PiLo = 6.4206383e-09f, k2Pi = 6.2831855f;
-  float thi[3], tlo[3];
+  constexpr int c_lo = 32 * HH, c_hi = 32 * HH + 31;
+  constexpr int k0 = c_lo < 3 ? 0 : (c_lo - 3) / 6;                        // first octave this thread touches
+  constexpr int k1 = (c_hi < 3 + 6 * L ? (c_hi - 3) / 6 : L - 1);          // last one
+  float sn[3][10], cs[3][10];
+  if (k0 <= k1) {
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    thi[j] = p[j] * kInv2PiHi;
-    tlo[j] = fmaf(p[j], kInv2PiHi, -thi[j]) + p[j] * kInv2PiLo;
+    for (int j = 0; j < 3; ++j) {
+      const float sc = (float)(1 << k0);
+      const float thi = p[j] * kInv2PiHi;
+      const float tlo = fmaf(p[j], kInv2PiHi, -thi) + p[j] * kInv2PiLo;
+      const float a = thi * sc;
+      const float f = ((a - rintf(a)) + tlo * sc) * k2Pi;
+      sn[j][k0] = __sinf(f);
+      cs[j][k0] = __cosf(f);
+#pragma unroll
+      for (int k = k0 + 1; k <= k1; ++k) {
+        sn[j][k] = 2.f * sn[j][k - 1] * cs[j][k - 1];
+        cs[j][k] = fmaf(-2.f * sn[j][k - 1], sn[j][k - 1], 1.f);
+      }
+    }
   }
   float e[32];
 #pragma unroll
@@ -188,10 +206,7 @@ __device__ __forceinline__ void encode_cols(const float (&p)[3], uint32_t (&pack
       e[i] = p[c];
     } else if (c < 3 + 6 * L) {
       const int k = (c - 3) / 6, r = (c - 3) % 6, j = r % 3;
-      const float sc = (float)(1 << k);
-      const float a = thi[j] * sc;
-      const float f = (a - rintf(a)) + tlo[j] * sc;
-      e[i] = (r < 3) ? __sinf(f * k2Pi) : __cosf(f * k2Pi);
+      e[i] = (r < 3) ? sn[j][k] : cs[j][k];
     } else {
       e[i] = 0.f;
     }
@@ -454,9 +469,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     // gamma(x) of tile t for LAYER 0 goes into chunk 0 of the tile's own activation buffer (free at that time), so
     // it can be produced right after the tile's last epilogue of the previous super-tile, under the other tile's
     // tail, instead of serialising both tiles through the shared enc buffer at the start of an iteration
-    auto write_first_layer_x = [&](int t, long long grow, uint8_t* gsave) {
-      float p[3];
-      load_point(grow, p);
+    auto write_first_layer_x = [&](int t, const float (&p)[3], uint8_t* gsave) {
       uint32_t w[16];
       if (hh == 0) encode_cols<10, 0>(p, w); else encode_cols<10, 1>(p, w);
       store_row32(smem + kSmAct + t * 4 * kChunkBytes, row, 4 * hh, w);
@@ -484,10 +497,13 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       const long long st0 = cluster_id;
       for (int t = 0; t < 2; ++t) {
         const long long g0 = st0 * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
-        write_first_layer_x(t, g0, SAVE ? a.acts + (size_t)(st0 * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
+        float p0[3];
+        load_point(g0, p0);
+        write_first_layer_x(t, p0, SAVE ? a.acts + (size_t)(st0 * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
         signal_ready(t);
       }
     }
+    float pnext[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // sample positions of my rows in the NEXT super-tile
     for (int it = 0; it < niter; ++it) {
       const long long st = cluster_id + (long long)it * a.nclusters;
       long long grow[2];
@@ -664,6 +680,8 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           }
           // ---- operands the NEXT layer needs besides the activations
           if (l == 4) { enc_wait(); write_enc_x(grow[t], nullptr); }
+          if (l == 6 && it + 1 < niter)       // global loads whose latency must not sit in front of the next encode
+            load_point((st + a.nclusters) * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row, pnext[t]);
           if (l == 8) { enc_wait(); write_enc_d(grow[t], SAVE ? gtile[t] + kFDg : nullptr); }
           if (et == 0) tr(2, 0x800 + l * 2 + t);
           if (l + 1 < sc.nlayers) {
@@ -678,7 +696,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const long long stn = st + a.nclusters;
-            write_first_layer_x(t, stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row,
+            write_first_layer_x(t, pnext[t],
                                 SAVE ? a.acts + (size_t)(stn * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
             signal_ready(t);
           } else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
