@@ -163,9 +163,16 @@ struct MlpArgs {
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
 };
 constexpr int kTraceLen = 4096;
+
+// The fp32 parameter block of the network a launch evaluates, ALSO in the constant bank: the final epilogue
+// (views bias, rgb head) reads it with compile-time offsets, so the values are constant-bank operands of the FMAs
+// instead of 64 broadcast LDS.128 per thread (that epilogue was bound by the shared-memory pipe).  One block per
+// process; launch_mlp copies into it in stream order and chains launches on different streams with an event.
+__constant__ float c_par[kParamFloats + 4];
 // Training tile stores are bulk (TMA) copies out of the activation buffers.  Writing them with 16-byte stores from the
 // epilogue registers was measured and rejected (forward+save 1.69 ms vs 1.02 ms, chain 2.09 vs 1.66 ms; profiles/README.md).
 static long long* g_trace = nullptr;
+static cudaEvent_t g_const_event = nullptr;   // recorded after every fused-MLP launch (guards c_par)
 
 // ------------------------------------------------------------- encoding
 // value of column c of gamma(p) (embedder.py:54-65): [p | sin f0 p | cos f0 p | sin f1 p | ...]
@@ -220,6 +227,32 @@ __device__ __forceinline__ void store_row32(uint8_t* chunk, int row, int unit0, 
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<uint4*>(chunk + sw128_offset(row, unit0 + i)) =
         make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+// rgb head of one sample from its 64 view-layer columns [64*HH, 64*HH+64): x = relu(acc + bias), partial
+// rgb[k] += x * W_rgb[k][col]; all weights are constant-bank operands (c_par, compile-time offsets).
+template <int HH, bool SAVE>
+__device__ __forceinline__ void rgb_head_half(const uint32_t (&v)[32], int b, float (&ca)[3], float (&cb)[3],
+                                              float (&xs)[32], uint32_t& signbits) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = 64 * HH + 32 * b + j;          // b is a compile-time constant at every call site (unrolled)
+    const float pre = __uint_as_float(v[j]) + c_par[kOffBiasViews + c];
+    if (SAVE) m = __funnelshift_l(__float_as_uint(pre), m, 1);
+    const float x = fmaxf(pre, 0.f);
+    xs[j] = x;
+    if (j & 1) {
+      cb[0] = fmaf(x, c_par[kOffRgbW + c], cb[0]);
+      cb[1] = fmaf(x, c_par[kOffRgbW + 128 + c], cb[1]);
+      cb[2] = fmaf(x, c_par[kOffRgbW + 256 + c], cb[2]);
+    } else {
+      ca[0] = fmaf(x, c_par[kOffRgbW + c], ca[0]);
+      ca[1] = fmaf(x, c_par[kOffRgbW + 128 + c], ca[1]);
+      ca[2] = fmaf(x, c_par[kOffRgbW + 256 + c], ca[2]);
+    }
+  }
+  signbits = m;
 }
 
 // -------------------------------------------------------------- kernel
@@ -625,45 +658,27 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             // view-layer columns 64*hh .. 64*hh+63; the hh == 1 partial rgb sums cross over through a scratch area
             // (the unused output_linear rows of the parameter block) and hh == 0 writes the sample's raw[4].
             {
-              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+              // (two accumulator sets per colour and both TMEM loads issued up front: this epilogue is bound by
+              //  instruction latency, not by TMEM bandwidth)
+              float ca[3] = {0.f, 0.f, 0.f}, cb[3] = {0.f, 0.f, 0.f};
               uint32_t sbits[2] = {0u, 0u};
-              const float* bias = s_par + kOffBiasViews + 64 * hh;
-              const float* rw = s_par + kOffRgbW + 64 * hh;
-#pragma unroll 1
+              uint32_t v2[2][32];
+              tmem_ld32(taddr + 64 * hh, v2[0]);
+              tmem_ld32(taddr + 64 * hh + 32, v2[1]);
+              tmem_ld_wait();
+#pragma unroll
               for (int b = 0; b < 2; ++b) {
-                uint32_t v[32];
-                tmem_ld32(taddr + 64 * hh + 32 * b, v);
-                tmem_ld_wait();
                 float xs[32];
-                uint32_t m = 0u;
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 bb = *reinterpret_cast<const float4*>(bias + 32 * b + 4 * j4);
-                  const float4 r0 = *reinterpret_cast<const float4*>(rw + 32 * b + 4 * j4);
-                  const float4 r1 = *reinterpret_cast<const float4*>(rw + 128 + 32 * b + 4 * j4);
-                  const float4 r2 = *reinterpret_cast<const float4*>(rw + 256 + 32 * b + 4 * j4);
-                  const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, q0[4] = {r0.x, r0.y, r0.z, r0.w};
-                  const float q1[4] = {r1.x, r1.y, r1.z, r1.w}, q2[4] = {r2.x, r2.y, r2.z, r2.w};
-#pragma unroll
-                  for (int jj = 0; jj < 4; ++jj) {
-                    const int j = 4 * j4 + jj;
-                    const float pre = __uint_as_float(v[j]) + bv[jj];
-                    if (SAVE) m = __funnelshift_l(__float_as_uint(pre), m, 1);
-                    const float x = fmaxf(pre, 0.f);
-                    xs[j] = x;
-                    c0 = fmaf(x, q0[jj], c0);
-                    c1 = fmaf(x, q1[jj], c1);
-                    c2 = fmaf(x, q2[jj], c2);
-                  }
-                }
-                if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients, and its sign bits
-                  sbits[b] = m;
+                if (hh == 0) rgb_head_half<0, SAVE>(v2[b], b, ca, cb, xs, sbits[b]);
+                else rgb_head_half<1, SAVE>(v2[b], b, ca, cb, xs, sbits[b]);
+                if (SAVE) {      // hv (bf16) for the rgb-head / views-layer gradients
                   uint32_t w[16];
 #pragma unroll
                   for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(xs[2 * i], xs[2 * i + 1]);
                   store_row32(gtile[t] + kFHv + hh * kPanel, row, 4 * b, w);
                 }
               }
+              const float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2];
               if (SAVE)
                 *reinterpret_cast<uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes + 8 * hh) =
                     make_uint2(sbits[0], sbits[1]);
@@ -1030,18 +1045,33 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
+  {  // parameter block -> constant bank, in stream order; launches on different streams are chained by an event
+    static cudaEvent_t last_done = nullptr;
+    static cudaStream_t last_stream = nullptr;
+    static std::mutex cmu;
+    std::lock_guard<std::mutex> clock_(cmu);
+    const cudaStream_t st = as_stream(stream);
+    if (last_done == nullptr) NERFB_CUDA(cudaEventCreateWithFlags(&last_done, cudaEventDisableTiming));
+    else if (last_stream != st) NERFB_CUDA(cudaStreamWaitEvent(st, last_done, 0));
+    NERFB_CUDA(cudaMemcpyToSymbolAsync(c_par, a.packed + a.param_off, kParamBytes, 0, cudaMemcpyDeviceToDevice, st));
+    last_stream = st;
+    g_const_event = last_done;
+  }
   BlobMaps maps_v{};
   const BlobMaps* maps = &maps_v;
   const size_t blob_bytes = (size_t)a.param_off + kParamBytes;
   if (int rc = get_blob_maps(a.packed, blob_bytes, &maps_v)) return rc;
   if (mode == MODE_FWD) {
     NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
+    NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD>");
   } else if (mode == MODE_FWD_SAVE) {
     NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64));
+    NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD_SAVE>");
   }
   NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64));
+  NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
   return check_launch("nerf_mlp_kernel<BWD>");
 }
 
