@@ -726,6 +726,8 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       // bulk-stores it for the weight-gradient kernel.
       const float* w_rgb = s_par + kOffRgbW;
       const float* w_alpha = s_par + kOffHeadW;
+      float4 dr_next[2];      // d_raw row and hv sign bits of my rows in the next super-tile, requested layers ahead
+      uint2 mhv_next[2];
       for (int it = 0; it < niter; ++it) {
         const long long st = cluster_id + (long long)it * a.nclusters;
         long long grow[2];
@@ -739,13 +741,19 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           gtile[t] = a.gstore + T * kBwdTileBytes;
         }
         float dsig[2];
+        if (it == 0) {        // first super-tile: nothing was prefetched yet
+          for (int t = 0; t < 2; ++t) {
+            dr_next[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow[t] < a.nrows) dr_next[t] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + grow[t]);
+            mhv_next[t] = __ldg(reinterpret_cast<const uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
+          }
+        }
         for (int t = 0; t < 2; ++t) {
           // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
-          float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (grow[t] < a.nrows) dr = __ldg(reinterpret_cast<const float4*>(a.d_raw) + grow[t]);
+          const float4 dr = dr_next[t];
           dsig[t] = dr.w;
           // hv sign bits: 4 words for columns 0..127; my chunk uses words 2*hh and 2*hh+1
-          const uint2 mhv = __ldg(reinterpret_cast<const uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
+          const uint2 mhv = mhv_next[t];
           uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {          // 32 columns at a time
@@ -762,6 +770,12 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           }
           publish(t, true, gtile[t] + kGHv, 2);
         }
+        // the 16 bytes of sign bits a thread needs for a tile-layer are requested one whole epilogue ahead (the chain
+        // is epilogue-bound, so a load issued right before its use would expose the full DRAM latency every time)
+        auto load_mask_words = [&](int jj, int tt) -> uint4 {
+          return __ldg(reinterpret_cast<const uint4*>(mtile[tt] + ((size_t)(8 - jj) * 128 + row) * kMaskRowBytes + 16 * hh));
+        };
+        uint4 mw_next = load_mask_words(1, 0);         // first masked tile-layer: j = 1, t = 0
         for (int j = 0; j < sc.nlayers; ++j) {
           const int m = 8 - j;                       // mask layer: j=1 -> h7 ... j=8 -> h0 ; j=0: feature (no ReLU)
           for (int t = 0; t < 2; ++t) {
@@ -771,9 +785,12 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
 #else
             const bool use_mask = j > 0;
 #endif
-            uint4 mw = make_uint4(0u, 0u, 0u, 0u);   // requested before the wait on the MMA: 16 bytes per thread
-            if (use_mask)
-              mw = __ldg(reinterpret_cast<const uint4*>(mtile[t] + ((size_t)m * 128 + row) * kMaskRowBytes + 16 * hh));
+            uint4 mw = make_uint4(0u, 0u, 0u, 0u);
+            if (use_mask) {
+              mw = mw_next;
+              const int jn = t == 0 ? j : j + 1, tn = t ^ 1;          // next masked tile-layer
+              if (jn < sc.nlayers) mw_next = load_mask_words(jn, tn);
+            }
             mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
             done_cnt[t]++;
             if (et == 0) tr(2, 0x700 + j * 2 + t);
@@ -801,6 +818,14 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1]));
               }
               if (use_mask) apply_sign_mask32(w, mwv[b]);
+            if (b == 3 && j == 6 && it + 1 < niter) {       // next super-tile's first-stage inputs, two layers early
+              const long long stn = st + a.nclusters;
+              const long long gn = stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
+              dr_next[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (gn < a.nrows) dr_next[t] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + gn);
+              mhv_next[t] = __ldg(reinterpret_cast<const uint2*>(a.masks + (size_t)(stn * 4 + 2 * t + rank) * kMaskTileBytes +
+                                                                  ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
+            }
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
               if (b == 1) store_first_panel(t, gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel));
