@@ -807,12 +807,16 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               if (b < 3) tmem_ld32(taddr + colbase + 32 * (b + 1), v[(b + 1) & 1]);
               const uint32_t (&vv)[32] = v[b & 1];
               uint32_t w[16];
-              if (j == 1) {
+              if (j == 1) {       // + d_sigma * w_alpha (vector loads: the shared-memory pipe is what this epilogue waits on)
                 const float* wa = w_alpha + colbase + 32 * b;
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  w[i] = pack_bf16x2(fmaf(ds, wa[2 * i], __uint_as_float(vv[2 * i])),
-                                     fmaf(ds, wa[2 * i + 1], __uint_as_float(vv[2 * i + 1])));
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * i4);
+                  w[2 * i4] = pack_bf16x2(fmaf(ds, a4.x, __uint_as_float(vv[4 * i4])),
+                                          fmaf(ds, a4.y, __uint_as_float(vv[4 * i4 + 1])));
+                  w[2 * i4 + 1] = pack_bf16x2(fmaf(ds, a4.z, __uint_as_float(vv[4 * i4 + 2])),
+                                              fmaf(ds, a4.w, __uint_as_float(vv[4 * i4 + 3])));
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1]));
