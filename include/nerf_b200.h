@@ -241,6 +241,36 @@ int nerfb_set_trace(long long* dev_buf);
  * before trapping when a barrier wait times out ([0]=0xDEAD when fired). */
 const unsigned long long* nerfb_watchdog_record(void);
 
+/* ---------------------------------------------------- keyed random draws */
+
+/* Random draws of render_rays keyed by (seed, GLOBAL ray index) -- SURVEY.md 8(e).
+ * Replaces torch.rand / torch.randn of ipynb:428-444 (t_rand), nerf_helpers.py:404 (u) and
+ * ipynb:312-325 (density noise), whose values depend on chunking and sharding.
+ * Value = f(seed, ray_offset + row, column, stream_id): Philox4x32-10 with
+ * counter (ray_lo, ray_hi, column/4, stream_id), key (seed_lo, seed_hi), word column%4;
+ * uniform = (word>>8) * 2^-24 in [0,1); normal = Box-Muller on word pairs, times `scale`. */
+enum { NERFB_RNG_T_RAND = 0, NERFB_RNG_U = 1, NERFB_RNG_NOISE_COARSE = 2, NERFB_RNG_NOISE_FINE = 3 };
+int nerfb_keyed_rng(unsigned long long seed, long long ray_offset, int R, int S, int stream_id,
+                    int normal, float scale, float* out /* [R,S] */, void* stream);
+/* All draws of one render_rays call in ONE launch; NULL outputs are skipped.
+ * t_rand [R,N_samples], u [R,N_importance] uniform; noise_coarse [R,N_samples],
+ * noise_fine [R,N_samples+N_importance] = N(0,1) * noise_std. */
+int nerfb_render_rays_rng(unsigned long long seed, long long ray_offset, int R, int N_samples,
+                          int N_importance, float noise_std, float* t_rand, float* u,
+                          float* noise_coarse, float* noise_fine, void* stream);
+
+/* -------------------------------------------------------- image metrics */
+
+/* calculate_metrics / calculate_ssim (nerf_helpers.py:21-111, 157-203) for two [H,W,C] fp32 images in one
+ * pass: out3 = { img2mse of the [0,1]-clipped images, mse2psnr of it, mean SSIM }.  SSIM: images clamped to
+ * [0,max_val], separable Gaussian window (filter_size odd <= 33, zero padding), variance clamps and constants
+ * of the reference.  ssim_map: optional [C,H,W] per-pixel map (the reference's return_map layout) or NULL.
+ * workspace: nerfb_image_metrics_workspace_bytes(H,W) bytes, 8-byte aligned.  Deterministic (fixed-order sums). */
+size_t nerfb_image_metrics_workspace_bytes(int H, int W);
+int nerfb_image_metrics(int H, int W, int C, const float* img1, const float* img2, float max_val,
+                        int filter_size, float filter_sigma, float k1, float k2, float* ssim_map,
+                        void* workspace, float* out3, void* stream);
+
 /* ------------------------------------------------------------- optimiser */
 
 /* torch.optim.Adam step (ipynb:905, 1275) for up to NERFB_ADAM_MAX tensors in

@@ -22,8 +22,11 @@ from .optim import FusedAdam  # noqa: F401
 from .render import (batchify, batchify_rays, create_nerf, get_rays, get_rays_np, img2mse, mse2psnr,  # noqa: F401
                      ndc_rays, raw2outputs, render, render_path, render_rays, run_network, sample_pdf, to8b)
 from .data import RayBatcher, precrop_pixel_ids  # noqa: F401
+from .metrics import calculate_lpips, calculate_metrics, calculate_ssim  # noqa: F401
+from .rng import keyed_rng, step_seed  # noqa: F401
 from . import ops  # noqa: F401
 
 __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network", "batchify", "raw2outputs",
            "create_nerf", "NeRF", "Embedder", "get_embedder", "get_rays", "get_rays_np", "ndc_rays", "sample_pdf",
-           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids"]
+           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids",
+           "keyed_rng", "step_seed", "calculate_ssim", "calculate_metrics", "calculate_lpips"]

@@ -55,6 +55,10 @@ _SIGS = {
     "nerfb_debug_schedule": ([_i] + [C.POINTER(_i)] * 6, _i),
     "nerfb_watchdog_record": ([], C.POINTER(C.c_ulonglong)),
     "nerfb_set_trace": ([_vp], _i),
+    "nerfb_keyed_rng": ([C.c_ulonglong, _ll, _i, _i, _i, _i, _f, _vp, _vp], _i),
+    "nerfb_render_rays_rng": ([C.c_ulonglong, _ll, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_image_metrics_workspace_bytes": ([_i, _i], C.c_size_t),
+    "nerfb_image_metrics": ([_i, _i, _i, _vp, _vp, _f, _i, _f, _f, _f, _vp, _vp, _vp, _vp], _i),
     "nerfb_adam_step": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll),
                          _f, _f, _f, _f, _i, _f, _vp], _i),
 }

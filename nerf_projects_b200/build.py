@@ -16,7 +16,7 @@ VARIANT = os.environ.get("NERFB_VARIANT", "")
 LIB = os.path.join(HERE, f"libnerf_b200_{VARIANT}.so" if VARIANT else "libnerf_b200.so")
 OBJ_DIR = os.path.join(HERE, "build", VARIANT) if VARIANT else os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "rays.cu", "embed.cu", "linear_fp32.cu", "composite.cu", "sample_pdf.cu", "adam.cu",
+SOURCES = ["api.cu", "rays.cu", "embed.cu", "linear_fp32.cu", "composite.cu", "sample_pdf.cu", "adam.cu", "rng.cu", "metrics.cu",
            "umma_selftest.cu", "mlp_tc.cu", "wgrad_tc.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -8,10 +8,13 @@ all-reduce of the flat parameter-gradient bucket per training step
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import rng as RNG
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int, int]:
@@ -22,12 +25,19 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int, int]:
     return lo, hi, per
 
 
-def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=None, return_packed=False, **kwargs):
+def _rng_ctx(rng_seed, lo):
+    """keyed_rng context positioned at the rank's first ray (draws independent of the world size)."""
+    return RNG.keyed_rng(rng_seed, ray_offset=lo) if rng_seed is not None else contextlib.nullcontext()
+
+
+def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=None, return_packed=False,
+                   rng_seed=None, **kwargs):
     """Ray-sharded render of one frame: each rank renders rays[lo:hi] with
     ``render_fn`` (= nerf_projects_b200.render), then one all_gather assembles
     [rgb(3), disp, acc] for the full frame on every rank.  With ``upload_to=device`` the rays
     are (pinned) host tensors and each rank copies only its own slice to its GPU.  Returns (rgb [N,3], disp [N], acc [N]) for the N input rays, or the
-    packed [N,5] tile tensor with ``return_packed=True``."""
+    packed [N,5] tile tensor with ``return_packed=True``.  ``rng_seed`` keys perturb / noise draws by
+    (seed, global ray index), so the frame does not depend on the number of ranks."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = rays_o.shape[0]
@@ -42,7 +52,8 @@ def render_sharded(render_fn, H, W, K, rays_o, rays_d, group=None, upload_to=Non
         my_d = rays_d[lo:hi].to(dev, non_blocking=True)
     tile = torch.zeros((per, 5), dtype=torch.float32, device=dev)
     if hi > lo:
-        rgb, disp, acc, _ = render_fn(H, W, K, rays=(my_o, my_d), **kwargs)
+        with _rng_ctx(rng_seed, lo):
+            rgb, disp, acc, _ = render_fn(H, W, K, rays=(my_o, my_d), **kwargs)
         tile[:hi - lo, 0:3] = rgb
         tile[:hi - lo, 3] = disp
         tile[:hi - lo, 4] = acc
@@ -89,15 +100,17 @@ class GradBucket:
 
 
 def train_step_sharded(render_fn, loss_fn, optimizer, bucket: GradBucket, H, W, K, rays_o, rays_d, target,
-                       group=None, **kwargs):
+                       group=None, rng_seed=None, **kwargs):
     """Data-parallel step: the global ray batch is split across ranks, each rank
     does forward/backward on its slice, gradients are averaged with one
-    all-reduce, every rank applies the identical Adam update."""
+    all-reduce, every rank applies the identical Adam update.  ``rng_seed`` (e.g.
+    ``rng.step_seed(seed, global_step)``) keys the perturb / noise draws by global ray index."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = rays_o.shape[0]
     lo, hi, _ = shard_bounds(n, world, rank)
-    rgb, disp, acc, extras = render_fn(H, W, K, rays=(rays_o[lo:hi], rays_d[lo:hi]), **kwargs)
+    with _rng_ctx(rng_seed, lo):
+        rgb, disp, acc, extras = render_fn(H, W, K, rays=(rays_o[lo:hi], rays_d[lo:hi]), **kwargs)
     loss = loss_fn(rgb, target[lo:hi])
     if "rgb0" in extras:
         loss = loss + loss_fn(extras["rgb0"], target[lo:hi])

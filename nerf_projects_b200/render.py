@@ -25,6 +25,8 @@ import torch
 from . import _lib as L
 from . import autograd as AG
 from . import mlp, ops
+from . import metrics as M
+from . import rng as RNG
 from .embedder import get_embedder
 from .model import NeRF
 
@@ -168,30 +170,14 @@ def _noise_std(v) -> float:
         return 0.0
 
 
-def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
-                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False,
-                pytest=False):
-    """ipynb:359-492.  Returns the reference's dict (rgb_map, disp_map, acc_map,
-    [raw], [rgb0, disp0, acc0, z_std]) plus additive keys depth_map / depth0."""
-    ray_batch = L.f32c(ray_batch)
-    L.require_cuda(ray_batch)
-    N_rays = ray_batch.shape[0]
-    spec = getattr(network_query_fn, "_nerfb", None)
-    fused = spec is not None and _fusable(network_fn, spec["embed_fn"], spec["embeddirs_fn"]) and \
-        (network_fine is None or _fusable(network_fine, spec["embed_fn"], spec["embeddirs_fn"])) and \
-        (ray_batch.shape[-1] > 8) == bool(network_fn.use_viewdirs)
-    if not fused:
-        return _render_rays_generic(ray_batch, network_fn, network_query_fn, N_samples, retraw, lindisp, perturb,
-                                    N_importance, network_fine, white_bkgd, raw_noise_std, pytest)
-    dev = ray_batch.device
-    perturb_on = bool(perturb > 0.)
+def _torch_draws(N_rays, N_samples, N_importance, perturb_on, std, dev, pytest):
+    """The reference's own draws (torch global generator; np.random.seed(0) under `pytest`)."""
     t_rand = u = noise_c = noise_f = None
     if perturb_on:
         t_rand = torch.rand((N_rays, N_samples), device=dev)
         if pytest:
             np.random.seed(0)
             t_rand = torch.tensor(np.random.rand(N_rays, N_samples), device=dev, dtype=torch.float32)
-    std = _noise_std(raw_noise_std)
 
     def mk_noise(S):
         if std <= 0.0:
@@ -209,6 +195,32 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             else:
                 u = torch.rand((N_rays, N_importance), device=dev)
         noise_f = mk_noise(N_samples + N_importance)
+    return t_rand, u, noise_c, noise_f
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False,
+                pytest=False):
+    """ipynb:359-492.  Returns the reference's dict (rgb_map, disp_map, acc_map,
+    [raw], [rgb0, disp0, acc0, z_std]) plus additive keys depth_map / depth0."""
+    ray_batch = L.f32c(ray_batch)
+    L.require_cuda(ray_batch)
+    N_rays = ray_batch.shape[0]
+    spec = getattr(network_query_fn, "_nerfb", None)
+    fused = spec is not None and _fusable(network_fn, spec["embed_fn"], spec["embeddirs_fn"]) and \
+        (network_fine is None or _fusable(network_fine, spec["embed_fn"], spec["embeddirs_fn"])) and \
+        (ray_batch.shape[-1] > 8) == bool(network_fn.use_viewdirs)
+    if not fused:
+        return _render_rays_generic(ray_batch, network_fn, network_query_fn, N_samples, retraw, lindisp, perturb,
+                                    N_importance, network_fine, white_bkgd, raw_noise_std, pytest)
+    dev = ray_batch.device
+    perturb_on = bool(perturb > 0.)
+    std = _noise_std(raw_noise_std)
+    if RNG.current() is not None and not pytest:
+        # draws keyed by (seed, global ray index): independent of chunking / sharding (rng.py)
+        t_rand, u, noise_c, noise_f = RNG.render_rays_draws(N_rays, N_samples, N_importance, perturb_on, std, dev)
+    else:
+        t_rand, u, noise_c, noise_f = _torch_draws(N_rays, N_samples, N_importance, perturb_on, std, dev, pytest)
     cfg = dict(network_fn=network_fn, network_fine=network_fine, N_samples=int(N_samples),
                N_importance=int(N_importance), lindisp=bool(lindisp), white_bkgd=bool(white_bkgd))
     params = list(network_fn.parameters())
@@ -235,33 +247,39 @@ def _render_rays_generic(ray_batch, network_fn, network_query_fn, N_samples, ret
                          N_importance, network_fine, white_bkgd, raw_noise_std, pytest):
     """Reference structure with arbitrary ``network_query_fn`` (ipynb:412-486)."""
     N_rays = ray_batch.shape[0]
+    dev = ray_batch.device
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
-    t_rand = None
-    if perturb > 0.:
-        t_rand = torch.rand((N_rays, N_samples), device=ray_batch.device)
-        if pytest:
-            np.random.seed(0)
-            t_rand = torch.tensor(np.random.rand(N_rays, N_samples), device=ray_batch.device, dtype=torch.float32)
+    keyed = RNG.current() is not None and not pytest
+    if keyed:
+        t_rand, u, noise_c, noise_f = RNG.render_rays_draws(N_rays, N_samples, N_importance, bool(perturb > 0.),
+                                                            _noise_std(raw_noise_std), dev)
+    else:
+        # the reference's order of draws: t_rand, coarse noise (inside raw2outputs), u, fine noise
+        t_rand = _torch_draws(N_rays, N_samples, 0, bool(perturb > 0.), 0.0, dev, pytest)[0]
+
+    def composite(raw, z, noise):
+        if keyed:
+            return AG.Raw2OutputsFn.apply(raw, z, rays_d, noise, bool(white_bkgd))
+        return raw2outputs(raw, z, rays_d, raw_noise_std, white_bkgd, pytest=pytest)
     z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand)
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
     raw = network_query_fn(pts, viewdirs, network_fn)
-    rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd,
-                                                                 pytest=pytest)
+    rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, noise_c if keyed else None)
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0, depth_0 = rgb_map, disp_map, acc_map, depth_map
-        u = None
-        if perturb > 0.:
-            u = torch.rand((N_rays, N_importance), device=ray_batch.device)
-            if pytest:
-                np.random.seed(0)
-                u = torch.tensor(np.random.rand(N_rays, N_importance), device=ray_batch.device, dtype=torch.float32)
+        if not keyed:
+            u = None
+            if perturb > 0.:
+                u = torch.rand((N_rays, N_importance), device=dev)
+                if pytest:
+                    np.random.seed(0)
+                    u = torch.tensor(np.random.rand(N_rays, N_importance), device=dev, dtype=torch.float32)
         z_vals, z_samples, z_std, _ = ops.hierarchical_z(z_vals, weights.detach(), N_importance, det=(u is None), u=u)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         run_fn = network_fn if network_fine is None else network_fine
         raw = network_query_fn(pts, viewdirs, run_fn)
-        rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd,
-                                                                     pytest=pytest)
+        rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, noise_f if keyed else None)
     ret = {"rgb_map": rgb_map, "disp_map": disp_map, "acc_map": acc_map}
     if retraw:
         ret["raw"] = raw
@@ -275,7 +293,8 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
     """ipynb:514-548."""
     all_ret = {}
     for i in range(0, rays_flat.shape[0], chunk):
-        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        with RNG.advanced(i):      # no-op unless a keyed_rng context is active
+            ret = render_rays(rays_flat[i:i + chunk], **kwargs)
         for k in ret:
             all_ret.setdefault(k, []).append(ret[k])
     return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
@@ -308,9 +327,11 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
                 calculate_metrics=False, metrics_include_lpips=True, metrics_device="cuda"):
     """ipynb:650-758.  The device->host copy of frame k overlaps the render of
-    frame k+1 (pinned buffers + a copy stream).  PSNR/MSE are computed when
-    ``calculate_metrics`` and ``gt_imgs`` are given; SSIM/LPIPS and PNG
-    writing are outside the hot path and need the optional dependencies."""
+    frame k+1 (pinned buffers + a copy stream).  With ``calculate_metrics`` and
+    ``gt_imgs``, MSE / PSNR / SSIM of every frame are computed on the GPU from the
+    frame where it lies (metrics.image_metrics, one fused pass, no host sync inside
+    the loop) and averaged like the reference: ``avg_/std_{psnr,ssim,mse[,lpips]}``.
+    LPIPS needs the optional ``lpips`` package (skipped with a warning otherwise)."""
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
@@ -322,7 +343,8 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
     pin = [(torch.empty((H, W, 3), dtype=torch.float32).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory())
            for _ in range(2)]
     pending = []
-    mses = []
+    frame_metrics = []          # device tensors [mse, psnr, ssim], read back once after the loop
+    lpips_vals = []
 
     def drain(upto):
         while len(pending) > upto:
@@ -342,7 +364,13 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
         rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
         if calculate_metrics and gt_imgs is not None and render_factor == 0 and i < len(gt_imgs):
             gt = torch.as_tensor(np.asarray(gt_imgs[i]), dtype=torch.float32, device=dev)[..., :3]
-            mses.append(img2mse(rgb, gt))
+            frame_metrics.append(M.image_metrics(rgb, gt)[0])
+            if metrics_include_lpips:
+                try:
+                    lpips_vals.append(M.calculate_lpips(rgb, gt, device=metrics_device))
+                except Exception as e:
+                    if not lpips_vals and i == 0:
+                        print(f"Warning: Could not calculate LPIPS: {e}")
         drain(1)
         slot = i % 2
         done = torch.cuda.Event()
@@ -357,11 +385,15 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
             ev.record(copy_stream)
         pending.append((i, ev, slot))
     drain(0)
-    if calculate_metrics and gt_imgs is not None and mses:
-        m = torch.stack(mses)
-        ps = mse2psnr(m)
-        avg = {"avg_mse": float(m.mean()), "std_mse": float(m.std(unbiased=False)),
-               "avg_psnr": float(ps.mean()), "std_psnr": float(ps.std(unbiased=False))}
+    if calculate_metrics and gt_imgs is not None:
+        avg = {}
+        if frame_metrics:
+            m = torch.stack(frame_metrics).double().cpu().numpy()      # [frames, 3] = mse, psnr, ssim
+            for j, key in enumerate(("mse", "psnr", "ssim")):
+                avg[f"avg_{key}"] = float(np.mean(m[:, j]))
+                avg[f"std_{key}"] = float(np.std(m[:, j]))
+        if lpips_vals:
+            avg["avg_lpips"], avg["std_lpips"] = float(np.mean(lpips_vals)), float(np.std(lpips_vals))
         return rgbs, disps, avg
     return rgbs, disps
 

@@ -330,3 +330,70 @@ def test_ray_batcher_modes():
         assert len(set(pix.tolist())) == 40, "pixels must be drawn without replacement"
         if i < 3:
             assert set(pix.tolist()) <= crop
+
+
+@pytest.mark.parametrize("R,S,off", [(1, 1, 0), (37, 64, 5), (300, 128, (1 << 33) + 11), (129, 63, 640000), (64, 192, 7)])
+def test_keyed_rng_bit_exact_vs_philox_oracle(R, S, off):
+    """csrc/rng.cu: uniform draws bit-exact against the numpy Philox4x32-10 restatement (pinned by Random123's
+    known answers in tests/test_philox_cpu.py); normals (Box-Muller, fp32 log/sincos) within 2e-6 relative."""
+    from nerf_projects_b200 import rng
+    from oracle import philox_np as P
+    seed = 0x1234_5678_9ABC_DEF0
+    for sid in (P.STREAM_T_RAND, P.STREAM_U):
+        got = rng.draw(R, S, sid, DEV, key=(seed, off)).cpu().numpy()
+        assert np.array_equal(got, P.keyed_uniform(seed, off, R, S, sid))
+    got = rng.draw(R, S, P.STREAM_NOISE_FINE, DEV, normal=True, scale=1.5, key=(seed, off)).cpu().numpy()
+    want = P.keyed_normal(seed, off, R, S, P.STREAM_NOISE_FINE, scale=1.5)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+
+
+def test_render_rays_rng_one_launch_equals_per_stream_draws():
+    from nerf_projects_b200 import rng
+    from oracle import philox_np as P
+    with rng.keyed_rng(99, ray_offset=1000):
+        t, u, nc, nf = rng.render_rays_draws(257, 64, 128, True, 0.5, DEV)
+        assert torch.equal(t, rng.draw(257, 64, P.STREAM_T_RAND, DEV))
+        assert torch.equal(u, rng.draw(257, 128, P.STREAM_U, DEV))
+        assert torch.equal(nc, rng.draw(257, 64, P.STREAM_NOISE_COARSE, DEV, normal=True, scale=0.5))
+        assert torch.equal(nf, rng.draw(257, 192, P.STREAM_NOISE_FINE, DEV, normal=True, scale=0.5))
+        assert rng.render_rays_draws(16, 64, 128, False, 0.0, DEV) == (None, None, None, None)
+        t2, u2, nc2, nf2 = rng.render_rays_draws(16, 64, 0, True, 0.0, DEV)
+        assert u2 is None and nc2 is None and nf2 is None and torch.equal(t2, t[:0].new_tensor(
+            P.keyed_uniform(99, 1000, 16, 64, P.STREAM_T_RAND)))
+    assert np.array_equal(t.cpu().numpy(), P.keyed_uniform(99, 1000, 257, 64, P.STREAM_T_RAND))
+
+
+def test_image_metrics_vs_reference_golden_and_oracle():
+    """csrc/metrics.cu through calculate_ssim / calculate_metrics (nerf_helpers.py:21-203): against the reference's own
+    outputs on the golden pairs (means 1e-5, per-pixel map 5e-4 -- ill-conditioned where the variance vanishes, see
+    test_oracle_vs_golden.py), non-default windows, an image smaller than the window; against the numpy oracle on a
+    full 800x800 frame; ndarray / CPU-tensor / CUDA-tensor inputs; bitwise run-to-run determinism."""
+    import os
+    import sys
+    import nerf_projects_b200 as nb
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden_metrics import CASES
+    from oracle import metrics_np as MO
+    g = gold("metrics")
+    for tag, (h, w, seed, kw) in CASES.items():
+        a, b = MO.synthetic_pair(h, w, seed)
+        assert abs(nb.calculate_ssim(a, b, **kw) - float(g[tag + ".ssim"])) < 1e-5, tag
+        m = nb.calculate_ssim(cu(a), torch.from_numpy(b), return_map=True, **kw)
+        assert tuple(m.shape) == g[tag + ".map"].shape and np.abs(npy(m) - g[tag + ".map"]).max() < 5e-4, tag
+        mm = nb.calculate_metrics(a, cu(b), include_lpips=False)
+        assert abs(mm["mse"] - float(g[tag + ".mse"])) < 1e-7 and abs(mm["psnr"] - float(g[tag + ".psnr"])) < 2e-5
+        assert abs(mm["ssim"] - float(g[tag + ".ssim_default"])) < 1e-5
+    a, b = MO.synthetic_pair(800, 800, 11)
+    want = MO.calculate_metrics(a, b)
+    got = nb.calculate_metrics(cu(a), cu(b), include_lpips=False)
+    for k in ("mse", "psnr", "ssim"):
+        assert abs(got[k] - want[k]) < 2e-5, (k, got[k], want[k])
+    from nerf_projects_b200 import metrics
+    o1, m1 = metrics.image_metrics(cu(a), cu(b), return_map=True)
+    o2, m2 = metrics.image_metrics(cu(a), cu(b), return_map=True)
+    assert torch.equal(o1, o2) and torch.equal(m1, m2)
+    assert abs(nb.calculate_ssim(a, a) - 1.0) < 1e-6
+    with pytest.raises(ValueError):
+        nb.calculate_ssim(a[None], b[None])
+    with pytest.raises(nb.NerfB200Error):
+        nb.calculate_ssim(a, b, filter_size=10)

@@ -115,3 +115,23 @@ def test_train_grads_match_reference():
             else:
                 np.testing.assert_allclose(gr.reshape(-1).numpy()[g[key + ".idx"]], g[key + ".val"],
                                            rtol=1e-3, atol=1e-7 + 1e-4 * n)
+
+
+def test_metrics_oracle_vs_reference_golden():
+    """oracle/metrics_np.py against the unmodified reference's calculate_ssim / calculate_metrics
+    (tests/golden/metrics.npz, tools/make_golden_metrics.py).  The per-pixel map is ill-conditioned where the local
+    variance vanishes (sigma = E[x^2] - mu^2 cancels; c2 = 9e-4), hence 5e-4 there and 1e-5 on the means."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden_metrics import CASES
+    from oracle import metrics_np as MO
+    g = gold("metrics")
+    for tag, (h, w, seed, kw) in CASES.items():
+        a, b = MO.synthetic_pair(h, w, seed)
+        assert abs(MO.calculate_ssim(a, b, **kw) - float(g[tag + ".ssim"])) < 1e-5
+        m = MO.calculate_ssim(a, b, return_map=True, **kw)
+        assert m.shape == g[tag + ".map"].shape and np.abs(m - g[tag + ".map"]).max() < 5e-4
+        mm = MO.calculate_metrics(a, b)
+        assert abs(mm["mse"] - float(g[tag + ".mse"])) < 1e-7 and abs(mm["psnr"] - float(g[tag + ".psnr"])) < 1e-5
+        assert abs(mm["ssim"] - float(g[tag + ".ssim_default"])) < 1e-5

@@ -62,6 +62,51 @@ def _worker(rank, world, port, n, out):
         dist.destroy_process_group()
 
 
+def _fake_render_keyed(H, W, K, rays=None, **kw):
+    """Stand-in render that reports the global ray index its keyed_rng context gives every ray."""
+    from nerf_projects_b200 import rng
+    ro, rd = rays
+    seed, off = rng.current()
+    idx = off + torch.arange(ro.shape[0], dtype=torch.float32)
+    return [ro * 0 + float(seed), idx, idx * 2, {}]
+
+
+def _worker_keyed(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nerf_projects_b200 import parallel, rng
+        ro = torch.zeros(n, 3)
+        rgb, disp, acc = parallel.render_sharded(_fake_render_keyed, 4, 4, None, ro, ro, rng_seed=77)
+        ok = torch.equal(disp, torch.arange(n, dtype=torch.float32)) and bool((rgb == 77).all()) and rng.current() is None
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_sharded_keys_draws_by_global_ray_index_gloo_world2():
+    """each rank's keyed_rng context starts at its first ray."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_keyed, args=(2, port, 33, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
+def test_keyed_rng_context_nesting_and_chunk_advance():
+    from nerf_projects_b200 import rng
+    assert rng.current() is None
+    with rng.keyed_rng(5, ray_offset=100):
+        assert rng.current() == (5, 100)
+        with rng.advanced(32):
+            assert rng.current() == (5, 132)
+        assert rng.current() == (5, 100)
+    assert rng.current() is None
+    with rng.advanced(3):                    # no active context: stays off
+        assert rng.current() is None
+    assert rng.step_seed(1, 0) != rng.step_seed(1, 1) and 0 <= rng.step_seed(1, 0) < 2 ** 64
+
+
 @pytest.mark.parametrize("n", [10, 33])
 def test_render_sharded_and_grad_bucket_gloo_world2(n):
     world = 2
