@@ -52,12 +52,13 @@ def peaks():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-    (profiles/traffic.json, written from an `ncu --set full` run of a bench-shaped launch); None if absent."""
+    (profiles/traffic.json, written from an `ncu --set full` run of a bench-shaped launch) as
+    (bytes per launch, provenance); (None, None) if absent."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
-        return None
+        return None, None
     t = json.load(open(path))
-    return {"bytes_per_launch": t["dram_bytes"], "launch": t["launch"], "source": t["source"]}
+    return t["dram_bytes"], {"unit": "bytes per launch", "launch": t["launch"], "source": t["source"]}
 
 
 def make_args():
@@ -314,7 +315,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "nerf_mlp_kernel<FWD>", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic()[0],
+                         "traffic_detail": ncu_traffic()[1],
                          "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                          "frac_of_burst_peak": achieved / pk["burst"],
                          "kernel_share_of_step": tot_ms / total_ms, "launches_timed": len(mlp_times),

@@ -1,0 +1,67 @@
+"""nerf_projects_b200.datasets (load_blender_data / load_llff_data / pose_spherical) against the outputs of the
+unmodified reference loaders on the same seeded directory trees (tests/golden/datasets.npz, written by
+tools/make_golden_datasets.py).  Host-side formats: everything bit-exact."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import datasets_synth as DS
+from _cases import gold
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def test_load_blender_data_vs_reference(tmp_path):
+    from nerf_projects_b200 import datasets as D
+    g = gold("datasets")
+    root = DS.write_blender(str(tmp_path / "blender"))
+    for tag, kw in (("b_full", dict(half_res=False, testskip=1)), ("b_half", dict(half_res=True, testskip=2)),
+                    ("b_skip0", dict(half_res=False, testskip=0))):
+        imgs, poses, rp, hwf, i_split = D.load_blender_data(root, **kw)
+        assert imgs.dtype == g[tag + ".imgs"].dtype and np.array_equal(imgs, g[tag + ".imgs"]), tag
+        assert poses.dtype == np.float32 and np.array_equal(poses, g[tag + ".poses"])
+        assert np.array_equal(rp.numpy(), g[tag + ".render_poses"]) and rp.shape == (40, 4, 4)
+        assert np.array_equal(np.array(hwf, np.float64), g[tag + ".hwf"])
+        for got, key in zip(i_split, ("i_train", "i_val", "i_test")):
+            assert np.array_equal(got, g[f"{tag}.{key}"])
+
+
+def test_pose_spherical_vs_reference():
+    from nerf_projects_b200 import datasets as D
+    g = gold("datasets")
+    got = np.stack([D.pose_spherical(a, p, r).numpy() for a, p, r in
+                    ((0., -30., 4.), (37.5, -30., 4.), (-180., 12., 2.5), (91., 0., 1.))])
+    assert np.array_equal(got, g["pose_spherical"])
+
+
+def test_load_llff_data_vs_reference(tmp_path):
+    from nerf_projects_b200 import datasets as D
+    g = gold("datasets")
+    root = DS.write_llff(str(tmp_path / "llff"))
+    for tag, kw in (("l_default", dict(factor=4)), ("l_spherify", dict(factor=4, spherify=True)),
+                    ("l_norecenter", dict(factor=4, recenter=False, bd_factor=None))):
+        with _quiet():
+            images, poses, bds, rp, i_test = D.load_llff_data(root, **kw)
+        assert images.dtype == np.float32 and np.array_equal(images, g[tag + ".images"]), tag
+        assert poses.dtype == np.float32 and np.array_equal(poses, g[tag + ".poses"]), tag
+        assert np.array_equal(bds, g[tag + ".bds"]) and np.array_equal(rp, g[tag + ".render_poses"]), tag
+        assert int(i_test) == int(g[tag + ".i_test"])
+    # hwf column: H, W of the minified images and focal / factor
+    assert tuple(poses[0, :, 4]) == (24.0, 32.0, 815.0 / 4)
+
+
+def test_llff_minify_when_directory_missing(tmp_path):
+    """A missing images_<factor> directory is produced (OpenCV area resize) with the right geometry."""
+    from nerf_projects_b200 import datasets as D
+    root = DS.write_llff(str(tmp_path / "llff"), H=8, W=12, n=3, factor=4)
+    with _quiet():
+        images, poses, *_ = D.load_llff_data(root, factor=2)
+    assert os.path.isdir(os.path.join(root, "images_2")) and images.shape == (3, 16, 24, 3)
+    assert tuple(poses[0, :, 4]) == (16.0, 24.0, 815.0 / 2)
+    with _quiet():
+        assert D._load_data(root, factor=None, load_imgs=False)[0].shape == (3, 5, 3)
