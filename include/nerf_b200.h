@@ -186,7 +186,8 @@ int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const flo
                        const float* pts, const float* viewdirs, int use_viewdirs, int out_ch,
                        const void* packed, float* raw, void* stream);
 /* ---- training: parameter gradients of the MLP on tensor cores (replaces the autograd graph of
- * NeRF.forward, nerf.py:57-111, under loss.backward(), ipynb:1274).  use_viewdirs networks only.
+ * NeRF.forward, nerf.py:57-111, under loss.backward(), ipynb:1274).  These three are for use_viewdirs networks;
+ * the *_nv_* variants below cover use_viewdirs=False.
  * Three launches per network pass and ray chunk:
  *   1. nerfb_mlp_fwd_save_bf16: the fused forward, which also bulk-stores every layer input as
  *      bf16 operand images into `acts` and one ReLU sign bit per hidden unit into `masks`;
@@ -209,6 +210,22 @@ int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* pa
                              const void* masks, void* gstore, void* stream);
 int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore,
                          const float* d_raw_padded, float* const* h_grads, void* stream);
+/* The same three steps for the network WITHOUT view directions (use_viewdirs=False: output_linear 256 -> out_ch on
+ * h7, nerf.py:50-55, 108-110): the forward-with-save stops after layer 7 (h7 is the last stored layer input, raw =
+ * [nrows, out_ch]); the chain starts from d_h7 = (d_raw W_out) * [h7 > 0] computed on CUDA cores and runs W7^T..W1^T;
+ * the weight-gradient launch has 10 jobs, output_linear's gradient being a CUDA-core reduction over the h7 tiles.
+ * d_raw is always [nrows,4] (channels 0..3); with out_ch = 5 the gradient of channel 4 is passed separately as
+ * d_raw4 [nrows] (d_raw4_padded: zero-padded to a multiple of 512 rows like d_raw_padded), else NULL.
+ * `acts` / `masks` / `gstore` have the sizes nerfb_train_store_bytes reports (same tile layout, view-layer panels unused). */
+int nerfb_mlp_fwd_save_nv_bf16(int R, int S, const float* rays, int ray_width, const float* z,
+                               const float* pts, int out_ch, const void* packed, float* raw,
+                               void* acts, void* masks, void* stream);
+int nerfb_pack_weights_bwd_nv(const float* const* h_params, int out_ch, void* packed_bwd, void* stream);
+int nerfb_mlp_bwd_chain_nv_bf16(long long nrows, const float* d_raw, const float* d_raw4,
+                                const void* packed_bwd, const void* masks, void* gstore, void* stream);
+int nerfb_mlp_wgrad_nv_bf16(long long nrows, int out_ch, const void* acts, const void* gstore,
+                            const float* d_raw_padded, const float* d_raw4_padded,
+                            float* const* h_grads, void* stream);
 /* Self-test of the tcgen05 building blocks (smem descriptors, 128B swizzle,
  * instruction descriptor, TMEM load layout, 2-CTA pairing):
  * C[M,N] = A[M,K] B[N,K]^T with bf16-rounded inputs and fp32 accumulation,
@@ -220,7 +237,7 @@ int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float
  * K multiple of 16 (<= 128), N multiple of 64 (<= 256), single CTA. */
 int nerfb_umma_selftest_mn(int N, int K, const float* At, const float* Bt, float* C, void* stream);
 /* Test hook (host only, no GPU): static schedule of the fused MLP kernel, which = 0 forward with view directions,
- * 1 forward without, 2 data-gradient chain.  h_loads: 2 ints per load {blob offset, bytes per CTA}; h_ops: 5 ints per
+ * 1 forward without, 2 data-gradient chain, 3 data-gradient chain without view directions.  h_loads: 2 ints per load {blob offset, bytes per CTA}; h_ops: 5 ints per
  * op {load, tile, A source chunk (4 = encoding buffer), flags (1 first, 2 last, 4 release slot, 8 release enc,
  * 16 N=128), block length on the first op of a block}.  Arrays must hold 44 loads / 84 ops. */
 int nerfb_debug_schedule(int which, int* h_nloads, int* h_nops, int* h_nlayers, int* h_loads, int* h_ops,

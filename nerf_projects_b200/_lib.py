@@ -48,6 +48,10 @@ _SIGS = {
     "nerfb_pack_weights_bwd": ([C.POINTER(_vp), _vp, _vp], _i),
     "nerfb_mlp_bwd_chain_bf16": ([_ll, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_mlp_wgrad_bf16": ([_ll, _vp, _vp, _vp, C.POINTER(_vp), _vp], _i),
+    "nerfb_mlp_fwd_save_nv_bf16": ([_i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_pack_weights_bwd_nv": ([C.POINTER(_vp), _i, _vp, _vp], _i),
+    "nerfb_mlp_bwd_chain_nv_bf16": ([_ll, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_mlp_wgrad_nv_bf16": ([_ll, _i, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp], _i),
     "nerfb_umma_selftest": ([_i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_umma_selftest_mn": ([_i, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_bulk_probe": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
@@ -81,6 +85,8 @@ def load():
             "(or __graft_entry__.build()).  There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (args, res) in _SIGS.items():
+        if _VARIANT and not hasattr(lib, name):
+            continue             # experiment builds of older sources may lack newer entry points
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.argtypes = args
         fn.restype = res

@@ -20,7 +20,7 @@ SOURCES = ["api.cu", "rays.cu", "embed.cu", "linear_fp32.cu", "composite.cu", "s
            "umma_selftest.cu", "mlp_tc.cu", "wgrad_tc.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NERFB_DEFINES", "").split()
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", CSRC] + os.environ.get("NERFB_DEFINES", "").split()
 
 
 def _nvcc() -> str:

@@ -73,6 +73,8 @@ constexpr int kMaskRowBytes = 32;
 constexpr int kMaskTileBytes = kMaskLayers * 128 * kMaskRowBytes;
 constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7^T..L1^T(28)
 constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
-enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2 };
+// *_NV: the network without view directions (output_linear head) -- separate instantiations, so the view-dependent
+// training kernels compile exactly as before
+enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2, MODE_FWD_SAVE_NV = 3, MODE_BWD_NV = 4 };
 
 }  // namespace nerfb

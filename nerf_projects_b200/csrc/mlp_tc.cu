@@ -118,9 +118,10 @@ static void build_schedule(bool vd, Sched& s) {
 }
 
 // backward chain: d_hv -> d_feature -> d_h7 -> ... -> d_h0 with transposed weights
-static void build_schedule_bwd(Sched& s) {
+// (vd == false: output_linear's data gradient is the first-stage operand, so the chain is W7^T .. W1^T only)
+static void build_schedule_bwd(bool vd, Sched& s) {
   s.nloads = s.nops = 0;
-  s.nlayers = 9;
+  s.nlayers = vd ? 9 : 7;
   auto add_load = [&](int id) -> uint8_t {
     s.loads[s.nloads] = LoadEnt{(uint32_t)id * kChunkFull, (uint32_t)kChunkBytes};
     return (uint8_t)s.nloads++;
@@ -130,14 +131,14 @@ static void build_schedule_bwd(Sched& s) {
   };
   int blk_first[48], blk_count[48], nblk = 0;
   auto block = [&](int first, int count) { blk_first[nblk] = first; blk_count[nblk++] = count; };
-  {  // views^T: K = 128 (two chunks)
+  if (vd) {  // views^T: K = 128 (two chunks)
     const uint8_t l0 = add_load(0), l1 = add_load(1);
     block(s.nops, 2);
     add_op(l0, 0, 0, F_FIRST); add_op(l1, 0, 1, F_LAST);
     block(s.nops, 2);
     add_op(l0, 1, 0, F_FIRST | F_REL_SLOT); add_op(l1, 1, 1, F_LAST | F_REL_SLOT);
   }
-  for (int j = 1; j <= 8; ++j) {
+  for (int j = vd ? 1 : 2; j <= 8; ++j) {      // j = 1: feature^T, j = 2..8: W7^T .. W1^T
     uint8_t l[4];
     for (int k = 0; k < 4; ++k) l[k] = add_load(2 + 4 * (j - 1) + k);
     block(s.nops, 4);
@@ -160,6 +161,7 @@ struct MlpArgs {
   uint8_t* masks;     // MODE_FWD_SAVE (out) / MODE_BWD (in): ReLU sign bits, [ntiles][kMaskTileBytes]
   uint8_t* gstore;    // MODE_BWD: [ntiles][kBwdTileBytes]
   const float* d_raw; // MODE_BWD: [nrows,4]
+  const float* d_raw4; // MODE_BWD without view directions: gradient of output channel 4 [nrows] or null
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
 };
 constexpr int kTraceLen = 4096;
@@ -260,8 +262,9 @@ template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc,
                 const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64) {
-  constexpr bool SAVE = (MODE == MODE_FWD_SAVE);
-  constexpr bool BWD = (MODE == MODE_BWD);
+  constexpr bool SAVE = (MODE == MODE_FWD_SAVE || MODE == MODE_FWD_SAVE_NV);
+  constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_BWD_NV);
+  constexpr bool NV = (MODE == MODE_FWD_SAVE_NV || MODE == MODE_BWD_NV);   // training kernels of the no-view-directions network
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -558,12 +561,14 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           if (et == 0) tr(2, 0x700 + l * 2 + t);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + t * 256;
-          if (l <= 8 && !(l == 7 && !vd)) {
+          if (l <= 8 && !(l == 7 && !vd && !(SAVE && NV))) {
             // ---- hidden layer: bias (+ReLU) -> bf16 -> next A operand; layer 7 also feeds the density head
             const float* bias = s_par + (l < 8 ? kOffBias + 256 * l : kOffBiasFeat) + 128 * hh;
             const float* hw = s_par + kOffHeadW + 128 * hh;
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
             float sig = 0.f;
+            float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // MODE_FWD_SAVE without view directions: output_linear partials
+            const bool out_head = SAVE && NV && l == 7;
             uint32_t sbits[4] = {0u, 0u, 0u, 0u};     // MODE_FWD_SAVE: sign bits of my 4 x 32 pre-activations
             // software pipeline: the TMEM load of batch b+1 is in flight while batch b is processed
             uint32_t v[2][32];
@@ -599,7 +604,15 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                   for (int k = 0; k < 4; ++k) m4[k] = __funnelshift_l(__float_as_uint(x[8 * k + jj]), m4[k], 1);
                 sbits[b] = (m4[0] << 24) | (m4[1] << 16) | (m4[2] << 8) | m4[3];
               }
-              if (l == 7) {
+              if (SAVE && NV && out_head) {
+                // output_linear (out_ch x 256) in fp32 from the un-rounded layer-7 activations, as in the plain forward
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float xr = fmaxf(x[j], 0.f);
+#pragma unroll
+                  for (int k = 0; k < 5; ++k) part[k] = fmaf(xr, hw[256 * k + 32 * b + j], part[k]);
+                }
+              } else if (l == 7) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   const float4 ww = *reinterpret_cast<const float4*>(hw + 32 * b + 4 * j4);
@@ -627,6 +640,18 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             if (SAVE && l < 8)
               *reinterpret_cast<uint4*>(mtile[t] + ((size_t)l * 128 + row) * kMaskRowBytes + 16 * hh) =
                   make_uint4(sbits[0], sbits[1], sbits[2], sbits[3]);
+            if (SAVE && NV && out_head) {
+              // the two column halves meet in the (idle) enc buffer: [tile][half][row][8]
+              float* xch = reinterpret_cast<float*>(smem + kSmEnc);
+#pragma unroll
+              for (int k = 0; k < 5; ++k) xch[((t * 2 + hh) * 128 + row) * 8 + k] = part[k];
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (hh == 0 && grow[t] < a.nrows) {
+                for (int k = 0; k < a.out_ch; ++k)
+                  a.raw[grow[t] * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
+                                                  xch[((t * 2 + 1) * 128 + row) * 8 + k] + s_par[kOffHeadB + k];
+              }
+            }
           } else if (l == 7) {
             // ---- no view directions: output_linear (out_ch x 256) in fp32 from layer-7 accumulators
             float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -704,17 +729,22 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             uint8_t* gdst = nullptr;
             if (SAVE) gdst = gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat);
             publish(t, true, gdst, 4);
-          } else if (it + 1 < niter) {
-            // last layer of this tile: its buffers are free -> layer-0 operand of the NEXT super-tile right away
-            if (SAVE) {           // ... once the bulk store of `feature` has left the buffer
-              if (half_leader) bulk_wait_read0();
-              asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            const long long stn = st + a.nclusters;
-            write_first_layer_x(t, pnext[t],
-                                SAVE ? a.acts + (size_t)(stn * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
-            signal_ready(t);
-          } else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+          } else {
+            // last layer of this tile.  Without view directions h7 is the last stored layer input: the second panels of
+            // both halves go out here (nothing to signal, no MMA follows).
+            if (SAVE && NV) publish(t, false, gtile[t] + kFH + 7 * 4 * kPanel, 4);
+            if (it + 1 < niter) {
+              // the tile's buffers are free -> layer-0 operand of the NEXT super-tile right away
+              if (SAVE) {           // ... once the bulk stores of the last stored layer have left the buffer
+                if (half_leader) bulk_wait_read0();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+              }
+              const long long stn = st + a.nclusters;
+              write_first_layer_x(t, pnext[t],
+                                  SAVE ? a.acts + (size_t)(stn * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
+              signal_ready(t);
+            } else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+          }
         }
       }
     }
@@ -724,10 +754,28 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       // mask of the layer it lands on (sign bits collected by the forward-with-save pass: 16 bytes per
       // thread and tile-layer, expanded with prmt), writes the bf16 gradient as the next A operand and
       // bulk-stores it for the weight-gradient kernel.
+      // Without view directions (MODE_BWD_NV) the first stage is d_h7 = (d_raw W_out) * [h7 > 0] on CUDA cores and the
+      // chain is W7^T .. W1^T (schedule layers j = 2..8).
+      constexpr bool vdb = !NV;
+      constexpr int j_first = vdb ? 0 : 2, j_end = 9;
       const float* w_rgb = s_par + kOffRgbW;
-      const float* w_alpha = s_par + kOffHeadW;
-      float4 dr_next[2];      // d_raw row and hv sign bits of my rows in the next super-tile, requested layers ahead
-      uint2 mhv_next[2];
+      const float* w_alpha = s_par + kOffHeadW;     // alpha_linear.weight, or output_linear.weight [5][256] (rows >= out_ch zero)
+      float4 dr_next[2];      // d_raw row and first-stage sign bits of my rows in the next super-tile, requested layers ahead
+      uint2 mhv_next[2];      // view layer: my 64 columns
+      uint4 mh7_next[2];      // no view directions: h7, my 128 columns
+      float d4_next[2] = {0.f, 0.f};   // no view directions, out_ch = 5: gradient of output channel 4
+      auto prefetch_first_stage = [&](long long stn, int t) {
+        const long long gn = stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
+        const uint8_t* mt = a.masks + (size_t)(stn * 4 + 2 * t + rank) * kMaskTileBytes;
+        dr_next[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        d4_next[t] = 0.f;
+        if (gn < a.nrows) {
+          dr_next[t] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + gn);
+          if (!vdb && a.d_raw4 != nullptr) d4_next[t] = __ldg(a.d_raw4 + gn);
+        }
+        if (vdb) mhv_next[t] = __ldg(reinterpret_cast<const uint2*>(mt + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
+        else mh7_next[t] = __ldg(reinterpret_cast<const uint4*>(mt + ((size_t)7 * 128 + row) * kMaskRowBytes + 16 * hh));
+      };
       for (int it = 0; it < niter; ++it) {
         const long long st = cluster_id + (long long)it * a.nclusters;
         long long grow[2];
@@ -742,16 +790,44 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         }
         float dsig[2];
         if (it == 0) {        // first super-tile: nothing was prefetched yet
-          for (int t = 0; t < 2; ++t) {
-            dr_next[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (grow[t] < a.nrows) dr_next[t] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + grow[t]);
-            mhv_next[t] = __ldg(reinterpret_cast<const uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
-          }
+          for (int t = 0; t < 2; ++t) prefetch_first_stage(st, t);
         }
         for (int t = 0; t < 2; ++t) {
-          // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
           const float4 dr = dr_next[t];
           dsig[t] = dr.w;
+          if (!vdb) {
+            // ---- d_h7 = (sum_k d_raw[k] W_out[k,:]) * [h7 > 0]: my 128 columns (chunks 2hh, 2hh+1) of the K=256 operand
+            const float d4 = d4_next[t];
+            const uint4 m7 = mh7_next[t];
+            const uint32_t m7v[4] = {m7.x, m7.y, m7.z, m7.w};
+            uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
+            uint8_t* gdst = gtile[t] + kGY + 7 * 4 * kPanel;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const float* wo = w_alpha + 128 * hh + 32 * b;
+              uint32_t w[16];
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                const float dk[5] = {dr.x, dr.y, dr.z, dr.w, d4};
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wo + 256 * k + 4 * i4);
+                  g[0] = fmaf(dk[k], w4.x, g[0]); g[1] = fmaf(dk[k], w4.y, g[1]);
+                  g[2] = fmaf(dk[k], w4.z, g[2]); g[3] = fmaf(dk[k], w4.w, g[3]);
+                }
+                w[2 * i4] = pack_bf16x2(g[0], g[1]);
+                w[2 * i4 + 1] = pack_bf16x2(g[2], g[3]);
+              }
+              apply_sign_mask32(w, m7v[b]);
+              const int col0 = 128 * hh + 32 * b;
+              store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
+              if (b == 1) store_first_panel(t, gdst);
+            }
+            publish(t, true, gdst, 4);
+            continue;
+          }
+          // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
           // hv sign bits: 4 words for columns 0..127; my chunk uses words 2*hh and 2*hh+1
           const uint2 mhv = mhv_next[t];
           uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
@@ -775,8 +851,8 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         auto load_mask_words = [&](int jj, int tt) -> uint4 {
           return __ldg(reinterpret_cast<const uint4*>(mtile[tt] + ((size_t)(8 - jj) * 128 + row) * kMaskRowBytes + 16 * hh));
         };
-        uint4 mw_next = load_mask_words(1, 0);         // first masked tile-layer: j = 1, t = 0
-        for (int j = 0; j < sc.nlayers; ++j) {
+        uint4 mw_next = load_mask_words(vdb ? 1 : 2, 0);         // first masked tile-layer: j = 1 (2 without views), t = 0
+        for (int j = j_first; j < j_end; ++j) {
           const int m = 8 - j;                       // mask layer: j=1 -> h7 ... j=8 -> h0 ; j=0: feature (no ReLU)
           for (int t = 0; t < 2; ++t) {
             const int colbase = 128 * hh;
@@ -789,7 +865,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             if (use_mask) {
               mw = mw_next;
               const int jn = t == 0 ? j : j + 1, tn = t ^ 1;          // next masked tile-layer
-              if (jn < sc.nlayers) mw_next = load_mask_words(jn, tn);
+              if (jn < j_end) mw_next = load_mask_words(jn, tn);
             }
             mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
             done_cnt[t]++;
@@ -822,21 +898,15 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1]));
               }
               if (use_mask) apply_sign_mask32(w, mwv[b]);
-            if (b == 3 && j == 6 && it + 1 < niter) {       // next super-tile's first-stage inputs, two layers early
-              const long long stn = st + a.nclusters;
-              const long long gn = stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
-              dr_next[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (gn < a.nrows) dr_next[t] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + gn);
-              mhv_next[t] = __ldg(reinterpret_cast<const uint2*>(a.masks + (size_t)(stn * 4 + 2 * t + rank) * kMaskTileBytes +
-                                                                  ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
-            }
+              if (b == 3 && j == 6 && it + 1 < niter)       // next super-tile's first-stage inputs, two layers early
+                prefetch_first_stage(st + a.nclusters, t);
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
               if (b == 1) store_first_panel(t, gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel));
             }
             if (et == 0) tr(2, 0x800 + j * 2 + t);
             uint8_t* gdst = gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);
-            publish(t, j + 1 < sc.nlayers, gdst, 4);
+            publish(t, j + 1 < j_end, gdst, 4);
           }
         }
       }
@@ -926,6 +996,7 @@ __global__ void pack_weights_bwd_kernel(const __grid_constant__ PackArgsT pt, co
   const int c = blockIdx.y;
   if (c < kNumBwdChunks) {
     const PackChunkT pc = pt.ch[c];
+    if (pc.w == nullptr) return;                   // chunk not used by this architecture (no view directions)
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 256 * 8; idx += gridDim.x * blockDim.x) {
       const int n = idx & 255, u = idx >> 8;       // n fastest: coalesced reads along a weight row
       float f[8];
@@ -1046,17 +1117,20 @@ static int get_blob_maps(const void* blob, size_t bytes, BlobMaps* out) {   // r
 }
 
 static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
-  static Sched sched_vd, sched_novd, sched_bwd;
+  static Sched sched_vd, sched_novd, sched_bwd, sched_bwd_novd;
   static bool init = false;
   static std::mutex mu;
   std::unique_lock<std::mutex> lock(mu);
   if (!init) {
     build_schedule(true, sched_vd);
     build_schedule(false, sched_novd);
-    build_schedule_bwd(sched_bwd);
+    build_schedule_bwd(true, sched_bwd);
+    build_schedule_bwd(false, sched_bwd_novd);
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     init = true;
   }
   lock.unlock();
@@ -1095,11 +1169,13 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD>");
   } else if (mode == MODE_FWD_SAVE) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64));
+    if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64));
+    else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE_NV>, a, sched_novd, maps->tm128, maps->tm64));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD_SAVE>");
   }
-  NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64));
+  if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64));
+  else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD_NV>, a, sched_bwd_novd, maps->tm128, maps->tm64));
   NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
   return check_launch("nerf_mlp_kernel<BWD>");
 }
@@ -1194,15 +1270,73 @@ extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, con
   return launch_mlp(MODE_BWD, a, true, stream);
 }
 
+// ---- the same three steps for the network WITHOUT view directions (output_linear head, nerf.py:50-55, 108-110)
+
+extern "C" int nerfb_mlp_fwd_save_nv_bf16(int R, int S, const float* rays, int ray_width, const float* z,
+                                          const float* pts, int out_ch, const void* packed, float* raw, void* acts,
+                                          void* masks, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && packed && raw && acts && masks, "nerfb_mlp_fwd_save_nv_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(packed) && aligned16(raw) && aligned16(acts) && aligned16(masks),
+                "nerfb_mlp_fwd_save_nv_bf16: packed / raw / acts / masks must be 16-byte aligned");
+  NERFB_REQUIRE(out_ch >= 1 && out_ch <= 5, "nerfb_mlp_fwd_save_nv_bf16: out_ch=%d unsupported", out_ch);
+  NERFB_REQUIRE(pts || (rays && z && ray_width >= 8), "nerfb_mlp_fwd_save_nv_bf16: need pts or rays+z");
+  if (R == 0) return NERFB_OK;
+  MlpArgs a{};
+  a.rays = rays; a.rw = ray_width; a.z = z; a.pts = pts; a.viewdirs = nullptr;
+  a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = 0;
+  a.packed = (const uint8_t*)packed; a.raw = raw; a.out_ch = out_ch;
+  a.param_off = kChunkAreaNoVD;
+  a.acts = (uint8_t*)acts;
+  a.masks = (uint8_t*)masks;
+  return launch_mlp(MODE_FWD_SAVE, a, false, stream);
+}
+
+extern "C" int nerfb_pack_weights_bwd_nv(const float* const* h_params, int out_ch, void* packed_bwd, void* stream) {
+  NERFB_REQUIRE(h_params && packed_bwd, "nerfb_pack_weights_bwd_nv: null argument");
+  for (int i = 0; i < 16; ++i) NERFB_REQUIRE(h_params[i], "nerfb_pack_weights_bwd_nv: pts_linears parameter %d missing", i);
+  NERFB_REQUIRE(out_ch >= 1 && out_ch <= 5 && h_params[NERFB_P_OUTPUT_W] && h_params[NERFB_P_OUTPUT_B],
+                "nerfb_pack_weights_bwd_nv: output_linear missing or out_ch=%d unsupported", out_ch);
+  PackArgsT pt{};
+  int n = 6;                                       // chunks 0..5 (views^T, feature^T) stay unused
+  for (int l = 7; l >= 1; --l)
+    for (int kc = 0; kc < 4; ++kc) pt.ch[n++] = PackChunkT{h_params[2 * l], l == 5 ? 319 : 256, 64 * kc, l == 5 ? 63 : 0};
+  PackArgs pa{};
+  pa.use_viewdirs = 0;
+  pa.out_ch = out_ch;                              // head block: output_linear rows 0..out_ch-1, zero above
+  for (int l = 0; l < 8; ++l) pa.bias[l] = h_params[2 * l + 1];
+  pa.src[0] = h_params[NERFB_P_OUTPUT_W];
+  pa.src[1] = h_params[NERFB_P_OUTPUT_B];
+  dim3 grid(2, kNumBwdChunks + 1);
+  pack_weights_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(pt, pa, (uint8_t*)packed_bwd);
+  return check_launch("pack_weights_bwd_kernel");
+}
+
+extern "C" int nerfb_mlp_bwd_chain_nv_bf16(long long nrows, const float* d_raw, const float* d_raw4, const void* packed_bwd,
+                                           const void* masks, void* gstore, void* stream) {
+  NERFB_REQUIRE(nrows >= 0 && d_raw && packed_bwd && masks && gstore, "nerfb_mlp_bwd_chain_nv_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(d_raw) && aligned16(packed_bwd) && aligned16(masks) && aligned16(gstore),
+                "nerfb_mlp_bwd_chain_nv_bf16: all buffers must be 16-byte aligned");
+  if (nrows == 0) return NERFB_OK;
+  MlpArgs a{};
+  a.nrows = nrows; a.S = 1; a.use_viewdirs = 0; a.out_ch = 4;
+  a.packed = (const uint8_t*)packed_bwd;
+  a.param_off = kChunkAreaBwd;
+  a.masks = (uint8_t*)masks;
+  a.gstore = (uint8_t*)gstore;
+  a.d_raw = d_raw;
+  a.d_raw4 = d_raw4;
+  return launch_mlp(MODE_BWD, a, false, stream);
+}
+
 /* Debug / test hook: the static schedule of a kernel mode (0 forward with view directions, 1 forward without,
- * 2 data-gradient chain) as flat int arrays -- loads: {blob offset, bytes per CTA}; ops: {load, tile, asrc, flags,
+ * 2 data-gradient chain, 3 data-gradient chain without view directions) as flat int arrays -- loads: {blob offset, bytes per CTA}; ops: {load, tile, asrc, flags,
  * block length (non-zero on the first op of a block)}.  Host only; lets the CPU test-suite check the ring invariants. */
 extern "C" int nerfb_debug_schedule(int which, int* h_nloads, int* h_nops, int* h_nlayers, int* h_loads, int* h_ops,
                                     int* h_ring_slots) {
-  NERFB_REQUIRE(which >= 0 && which <= 2 && h_nloads && h_nops && h_nlayers && h_loads && h_ops && h_ring_slots,
+  NERFB_REQUIRE(which >= 0 && which <= 3 && h_nloads && h_nops && h_nlayers && h_loads && h_ops && h_ring_slots,
                 "nerfb_debug_schedule: bad arguments");
   static Sched s;
-  if (which == 2) build_schedule_bwd(s); else build_schedule(which == 0, s);
+  if (which >= 2) build_schedule_bwd(which == 2, s); else build_schedule(which == 0, s);
   *h_nloads = s.nloads; *h_nops = s.nops; *h_nlayers = s.nlayers; *h_ring_slots = kNS;
   for (int i = 0; i < s.nloads; ++i) { h_loads[2 * i] = (int)s.loads[i].off; h_loads[2 * i + 1] = (int)s.loads[i].bytes; }
   for (int i = 0; i < s.nops; ++i) {

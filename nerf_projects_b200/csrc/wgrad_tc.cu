@@ -43,7 +43,7 @@ constexpr int kWgSmemBytes = kWgSmBars + 128;
 static_assert(kWgSmemBytes <= 232448, "shared memory budget exceeded");
 static_assert(kStageStride % 1024 == 0, "stage buffers must keep the swizzle phase");
 
-enum { SIMT_NONE = 0, SIMT_ALPHA = 1, SIMT_RGB = 2 };
+enum { SIMT_NONE = 0, SIMT_ALPHA = 1, SIMT_RGB = 2, SIMT_OUT = 3 };
 
 // 16-byte vector reduction into global memory (one L2 atomic operation for four floats)
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -72,6 +72,8 @@ struct WArgs {
   const uint8_t* acts;
   const uint8_t* gstore;
   const float* d_raw;      // [ntiles*128, 4], zero beyond the real rows
+  const float* d_raw4;     // SIMT_OUT with out_ch = 5: gradient of output channel 4, [ntiles*128] (zero padded) or null
+  int out_ch;              // SIMT_OUT: rows of output_linear
   long long nstages;       // 2 per 128-sample tile
   int cta_begin[kMaxJobs + 1];   // CTAs [cta_begin[j], cta_begin[j+1]) split job j's stages evenly: ONE work item per CTA
   Watch watch;
@@ -121,7 +123,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
         if (g >= kWgStages) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((g / kWgStages) + 1) & 1), a.watch, 0x1100 + jmine);
         const uint32_t dst = sbase + slot * kStageStride;
         const uint32_t fb = bar(B_FULL + slot);
-        mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u);
+        mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u +
+                                      ((jb.simt == SIMT_OUT && a.d_raw4 != nullptr) ? (uint32_t)kStageRows * 4u : 0u));
         const size_t tile = (size_t)(s >> 1), half = (size_t)(s & 1) * kHalfPanel;
         const uint8_t* gt = a.gstore + tile * kBwdTileBytes + jb.a_off + half;
         const uint8_t* ft = a.acts + tile * kFwdTileBytes + half;
@@ -133,6 +136,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
         for (int i = 0; i < jb.x_panels; ++i, ++p)
           bulk_g2s(dst + p * kHalfPanel, ft + jb.x_off + (size_t)i * kPanel, kHalfPanel, fb);
         bulk_g2s(dst + kStageDraw, a.d_raw + (size_t)s * kStageRows * 4, 1024, fb);
+        if (jb.simt == SIMT_OUT && a.d_raw4 != nullptr)      // channel 4 slice [64] fp32 behind the 4 staged h7 panels
+          bulk_g2s(dst + 4 * kHalfPanel, a.d_raw4 + (size_t)s * kStageRows, kStageRows * 4, fb);
       }
     }
   } else if (warp == 1) {
@@ -179,12 +184,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
       // per-thread SIMT accumulators.  Mapping for 4-panel operands: 16-byte unit u = st_id & 7 (8 columns)
       // of panel (st_id >> 3) & 3, rows r = (st_id >> 5) mod 4; a warp reads 4 full 128-byte rows per LDS.128.
       float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias: 8 columns of dY
-      float hs[3][8];                                              // head weight gradients
+      float hs[5][8];                                              // head weight gradients
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < 5; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) hs[k][i] = 0.f;
-      float hb[4] = {0.f, 0.f, 0.f, 0.f};                          // sums of d_raw components (thread 0)
+      float hb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};                     // sums of d_raw components (thread 0)
       const int su = st_id & 7;
       // dY has 4 panels (rows r = rg4 mod 4) or 2 panels (rows r = rg8 mod 8)
       const int bpan = jb.a_panels == 4 ? (st_id >> 3) & 3 : (st_id >> 3) & 1;
@@ -234,6 +239,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
           }
           if (st_id == 0)
             for (int r = 0; r < kStageRows; ++r) { hb[0] += draw[r].x; hb[1] += draw[r].y; hb[2] += draw[r].z; }
+        } else if (jb.simt == SIMT_OUT) {
+          // d output_linear.weight[k][c] += sum_r d_raw[r][k] * h7[r][c]   (h7 = the 4 staged panels; no MMA in this job)
+          const uint8_t* px = stp + ((st_id >> 3) & 3) * kHalfPanel;
+          const float* d4 = a.d_raw4 != nullptr ? reinterpret_cast<const float*>(stp + 4 * kHalfPanel) : nullptr;
+#pragma unroll 2
+          for (int r = st_id >> 5; r < kStageRows; r += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(px + r * 128 + ((su ^ (r & 7)) << 4));
+            const float4 d = draw[r];
+            acc8(hs[0], v, d.x); acc8(hs[1], v, d.y); acc8(hs[2], v, d.z); acc8(hs[3], v, d.w);
+            if (d4 != nullptr) acc8(hs[4], v, d4[r]);
+          }
+          if (st_id == 0)
+            for (int r = 0; r < kStageRows; ++r) {
+              hb[0] += draw[r].x; hb[1] += draw[r].y; hb[2] += draw[r].z; hb[3] += draw[r].w;
+              if (d4 != nullptr) hb[4] += d4[r];
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_EMPTY + slot));
@@ -254,6 +275,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
           for (int i = 0; i < 8; ++i) atomicAdd(jb.head_w + k * 128 + 64 * ((st_id >> 3) & 1) + 8 * su + i, hs[k][i]);
         if (st_id == 0)
           for (int k = 0; k < 3; ++k) atomicAdd(jb.head_b + k, hb[k]);
+      } else if (jb.simt == SIMT_OUT) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          if (k < a.out_ch) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(jb.head_w + k * 256 + 64 * ((st_id >> 3) & 3) + 8 * su + i, hs[k][i]);
+            if (st_id == 0) atomicAdd(jb.head_b + k, hb[k]);
+          }
+        }
       }
       // ---- drain the accumulators: dW[out, col_off + c] += D[out, c]
       mbar_wait(bar(B_ACC), 0u, a.watch, 0x1500 + j);
@@ -297,15 +327,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) nerf_wgrad_kernel(const __grid_
 
 using namespace nerfb;
 
-extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore, const float* d_raw_padded,
-                                    float* const* h_grads, void* stream) {
-  NERFB_REQUIRE(nrows >= 0 && acts && gstore && d_raw_padded && h_grads, "nerfb_mlp_wgrad_bf16: bad arguments");
-  NERFB_REQUIRE(aligned16(acts) && aligned16(gstore) && aligned16(d_raw_padded),
-                "nerfb_mlp_wgrad_bf16: acts / gstore / d_raw_padded must be 16-byte aligned");
-  for (int i = 0; i < NERFB_P_OUTPUT_W; ++i)
-    NERFB_REQUIRE(h_grads[i] == nullptr || aligned16(h_grads[i]), "nerfb_mlp_wgrad_bf16: gradient tensor %d is not 16-byte aligned", i);
-  for (int i = 0; i < NERFB_P_OUTPUT_W; ++i)
-    NERFB_REQUIRE(h_grads[i], "nerfb_mlp_wgrad_bf16: gradient tensor %d missing", i);
+// use_viewdirs != 0: 12 jobs (pts layers, feature + alpha head, views + rgb head); else 10 jobs (pts layers and a
+// CUDA-core-only job for output_linear from the staged h7 panels)
+static int launch_wgrad(const char* who, long long nrows, int use_viewdirs, int out_ch, const void* acts, const void* gstore,
+                        const float* d_raw_padded, const float* d_raw4_padded, float* const* h_grads, void* stream) {
+  NERFB_REQUIRE(nrows >= 0 && acts && gstore && d_raw_padded && h_grads, "%s: bad arguments", who);
+  NERFB_REQUIRE(aligned16(acts) && aligned16(gstore) && aligned16(d_raw_padded) && aligned16(d_raw4_padded),
+                "%s: acts / gstore / d_raw_padded must be 16-byte aligned", who);
+  for (int i = 0; i < NERFB_NUM_PARAMS; ++i) {
+    const bool needed = i < 16 || (use_viewdirs ? i < NERFB_P_OUTPUT_W : i >= NERFB_P_OUTPUT_W);
+    if (!needed) continue;
+    NERFB_REQUIRE(h_grads[i], "%s: gradient tensor %d missing", who, i);
+    NERFB_REQUIRE(aligned16(h_grads[i]), "%s: gradient tensor %d is not 16-byte aligned", who, i);
+  }
   if (nrows == 0) return NERFB_OK;
   WArgs a{};
   int n = 0;
@@ -343,13 +377,21 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
       a.jobs[n++] = plain(dY + l * 4 * kPanel, hL + (l - 1) * 4 * kPanel, G(2 * l), 256, 0, G(2 * l + 1));
     }
   }
-  {  // feature_linear (+ alpha_linear on CUDA cores from the same h7 tiles)
+  if (!use_viewdirs) {  // output_linear on CUDA cores from the h7 tiles (staged as "extra" panels; the job has no MMA)
+    WJob j{};
+    j.x_off = hL + 7 * 4 * kPanel; j.x_panels = 4;
+    j.simt = SIMT_OUT;
+    j.head_w = G(NERFB_P_OUTPUT_W); j.head_b = G(NERFB_P_OUTPUT_B);
+    j.weight = narrow_w;
+    a.jobs[n++] = j;
+  }
+  if (use_viewdirs) {  // feature_linear (+ alpha_linear on CUDA cores from the same h7 tiles)
     WJob j = plain(kGFeat, hL + 7 * 4 * kPanel, G(NERFB_P_FEATURE_W), 256, 0, G(NERFB_P_FEATURE_B));
     j.simt = SIMT_ALPHA;
     j.head_w = G(NERFB_P_ALPHA_W); j.head_b = G(NERFB_P_ALPHA_B);
     a.jobs[n++] = j;
   }
-  {  // views_linears.0: dhv^T [feature | gamma(d)]  (+ rgb_linear on CUDA cores from hv)
+  if (use_viewdirs) {  // views_linears.0: dhv^T [feature | gamma(d)]  (+ rgb_linear on CUDA cores from hv)
     WJob j{};
     j.a_off = kGHv; j.a_panels = 2;
     j.b_off[0] = kFFeat; j.b_panels[0] = 4; j.col_off[0] = 0; j.ncols[0] = 256;
@@ -366,6 +408,8 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
   a.acts = (const uint8_t*)acts;
   a.gstore = (const uint8_t*)gstore;
   a.d_raw = d_raw_padded;
+  a.d_raw4 = d_raw4_padded;
+  a.out_ch = out_ch;
   a.nstages = 8 * ((nrows + kSuperRows - 1) / kSuperRows);    // 4 tiles x 2 stages per 512-row super-tile
   a.watch = get_watch();
   static bool attr_set = false;
@@ -401,4 +445,18 @@ extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const voi
   }
   nerf_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, as_stream(stream)>>>(a);
   return check_launch("nerf_wgrad_kernel");
+}
+
+extern "C" int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore, const float* d_raw_padded,
+                                    float* const* h_grads, void* stream) {
+  return launch_wgrad("nerfb_mlp_wgrad_bf16", nrows, 1, 4, acts, gstore, d_raw_padded, nullptr, h_grads, stream);
+}
+
+extern "C" int nerfb_mlp_wgrad_nv_bf16(long long nrows, int out_ch, const void* acts, const void* gstore,
+                                       const float* d_raw_padded, const float* d_raw4_padded, float* const* h_grads,
+                                       void* stream) {
+  NERFB_REQUIRE(out_ch >= 1 && out_ch <= 5, "nerfb_mlp_wgrad_nv_bf16: out_ch=%d unsupported", out_ch);
+  NERFB_REQUIRE(out_ch < 5 || d_raw4_padded != nullptr, "nerfb_mlp_wgrad_nv_bf16: out_ch=5 needs d_raw4_padded");
+  return launch_wgrad("nerfb_mlp_wgrad_nv_bf16", nrows, 0, out_ch, acts, gstore, d_raw_padded,
+                      out_ch == 5 ? d_raw4_padded : nullptr, h_grads, stream);
 }

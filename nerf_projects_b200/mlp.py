@@ -238,7 +238,10 @@ def packed_weights_bwd(net) -> torch.Tensor:
     nbytes = ops.packed_weights_bwd_bytes()
     if cached is None or cached.numel() != nbytes or cached.device != dev:
         cached = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    ops.pack_weights_bwd(_param_ptrs(params), cached)
+    if net.use_viewdirs:
+        ops.pack_weights_bwd(_param_ptrs(params), cached)
+    else:
+        ops.pack_weights_bwd_nv(_param_ptrs(params), net.output_ch, cached)
     net._packed_bwd, net._packed_bwd_key = cached, key
     return cached
 
@@ -284,7 +287,42 @@ def _zero_grads(net) -> Dict[str, torch.Tensor]:
 
 
 def supports_bf16_backward(net) -> bool:
-    return bool(net.is_canonical() and net.use_viewdirs)
+    """Canonical 8x256 network, with view directions or with the plain output_linear head (4 or 5 channels)."""
+    return bool(net.is_canonical() and (net.use_viewdirs or net.output_ch in (4, 5)))
+
+
+def _raw_ch(net) -> int:
+    return 4 if net.use_viewdirs else net.output_ch
+
+
+def _padded_d_raw(net, d_raw, n, dev):
+    """d_raw [n,ch] -> ([npad,4] channels 0..3, [npad] channel 4 or None), zero beyond n (npad: whole 512-row super-tiles)."""
+    npad = (n + 511) // 512 * 512
+    ch = _raw_ch(net)
+    d_raw = L.f32c(d_raw).view(-1, ch)
+    d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
+    d_pad[:n].copy_(d_raw[:, :4])
+    d4 = None
+    if ch == 5:
+        d4 = torch.zeros(npad, dtype=torch.float32, device=dev)
+        d4[:n].copy_(d_raw[:, 4])
+    return d_pad, d4
+
+
+def _fwd_save(net, R, S, rays, z, pts, viewdirs, packed, raw, acts, masks):
+    if net.use_viewdirs:
+        ops.mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed, raw, acts, masks)
+    else:
+        ops.mlp_fwd_save_nv_bf16(R, S, rays, z, pts, net.output_ch, packed, raw, acts, masks)
+
+
+def _chain_and_wgrad(net, n, d_pad, d4, packed_bwd, acts, masks, gstore, gptrs):
+    if net.use_viewdirs:
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore)
+        ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs)
+    else:
+        ops.mlp_bwd_chain_nv_bf16(n, d_pad, d4, packed_bwd, masks, gstore)
+        ops.mlp_wgrad_nv_bf16(n, net.output_ch, acts, gstore, d_pad, d4, gptrs)
 
 
 def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.Tensor]:
@@ -292,7 +330,7 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
     is re-run with its layer inputs stored (recompute), then the data-gradient chain, then the
     weight-gradient GEMMs.  Nothing is kept between forward and backward except rays, z and d_raw."""
     if not supports_bf16_backward(net):
-        raise L.NerfB200Error("the tensor-core backward supports the canonical use_viewdirs network only")
+        raise L.NerfB200Error("the tensor-core backward supports the canonical 8x256 network only")
     dev = net.pts_linears[0].weight.device
     named = dict(net.named_parameters())
     grads = _zero_grads(net)
@@ -301,18 +339,16 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
     nchunk = max(1, -(-(R * S) // TRAIN_ROWS_PER_CHUNK))       # even split: no tiny tail chunk
     step = -(-R // nchunk)
     acts, gstore, masks = _train_workspace(dev, min(R, step) * S)
-    d_raw = L.f32c(d_raw).view(-1, 4)
+    ch = _raw_ch(net)
+    d_raw = L.f32c(d_raw).view(-1, ch)
     for r0 in range(0, R, step):
         r1 = min(R, r0 + step)
         n = (r1 - r0) * S
-        npad = (n + 511) // 512 * 512
-        d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
-        d_pad[:n].copy_(d_raw[r0 * S:r1 * S])
-        raw_tmp = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        ops.mlp_fwd_save_bf16(r1 - r0, S, _slice_rows(rays, r0, r1), _slice_rows(z, r0, r1),
-                              _slice_rows(pts, r0, r1, S), _slice_rows(viewdirs, r0, r1), packed, raw_tmp, acts, masks)
-        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore)
-        ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs)
+        d_pad, d4 = _padded_d_raw(net, d_raw[r0 * S:r1 * S], n, dev)
+        raw_tmp = torch.empty((n, ch), dtype=torch.float32, device=dev)
+        _fwd_save(net, r1 - r0, S, _slice_rows(rays, r0, r1), _slice_rows(z, r0, r1), _slice_rows(pts, r0, r1, S),
+                  _slice_rows(viewdirs, r0, r1), packed, raw_tmp, acts, masks)
+        _chain_and_wgrad(net, n, d_pad, d4, packed_bwd, acts, masks, gstore, gptrs)
     return grads
 
 
@@ -331,10 +367,10 @@ def forward_save_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
     -> (raw, (acts, masks))."""
     dev = net.pts_linears[0].weight.device
     n = R * S
-    raw = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    raw = torch.empty((n, _raw_ch(net)), dtype=torch.float32, device=dev)
     acts = torch.empty(ops.train_store_bytes(n, 0), dtype=torch.uint8, device=dev)
     masks = torch.empty(ops.train_store_bytes(n, 2), dtype=torch.uint8, device=dev)
-    ops.mlp_fwd_save_bf16(R, S, rays, z, pts, viewdirs, packed_weights(net), raw, acts, masks)
+    _fwd_save(net, R, S, rays, z, pts, viewdirs, packed_weights(net), raw, acts, masks)
     return raw, (acts, masks)
 
 
@@ -343,17 +379,14 @@ def backward_from_saved(net, nrows: int, saved, d_raw) -> Dict[str, torch.Tensor
     acts, masks = saved
     dev = acts.device
     grads = _zero_grads(net)
-    npad = (nrows + 511) // 512 * 512
-    d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
-    d_pad[:nrows].copy_(L.f32c(d_raw).view(-1, 4))
+    d_pad, d4 = _padded_d_raw(net, d_raw, nrows, dev)
     _, gstore, _ = _train_workspace(dev, nrows, need_acts=False)
-    ops.mlp_bwd_chain_bf16(nrows, d_pad, packed_weights_bwd(net), masks, gstore)
-    ops.mlp_wgrad_bf16(nrows, acts, gstore, d_pad, _param_ptrs(grads))
+    _chain_and_wgrad(net, nrows, d_pad, d4, packed_weights_bwd(net), acts, masks, gstore, _param_ptrs(grads))
     return grads
 
 
 def backward(net, R, S, rays, z, pts, viewdirs, d_raw):
-    """bf16 mode: tensor-core backward for the canonical view-dependent network, fp32 CUDA-core kernels
+    """bf16 mode: tensor-core backward for the canonical 8x256 network (either head), fp32 CUDA-core kernels
     otherwise (other architectures, validation mode)."""
     if _PRECISION == "bf16" and supports_bf16_backward(net):
         return backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw)

@@ -310,6 +310,36 @@ def mlp_wgrad_bf16(nrows, acts, gstore, d_raw_padded, grad_ptrs: Sequence[Option
     _count()
 
 
+# no view directions (output_linear head): d_raw is [nrows,4] = channels 0..3, d_raw4 [nrows] = channel 4 or None
+
+def pack_weights_bwd_nv(param_ptrs: Sequence[Optional[int]], out_ch: int, packed_bwd: torch.Tensor):
+    arr = (C.c_void_p * L.NERFB_NUM_PARAMS)(*[p if p else None for p in param_ptrs])
+    L.check(L.load().nerfb_pack_weights_bwd_nv(arr, int(out_ch), L.ptr(packed_bwd), L.stream()),
+            "nerfb_pack_weights_bwd_nv")
+    _count()
+
+
+def mlp_fwd_save_nv_bf16(R, S, rays, z, pts, out_ch, packed, raw, acts, masks):
+    L.check(L.load().nerfb_mlp_fwd_save_nv_bf16(int(R), int(S), L.ptr(rays), rays.shape[1] if rays is not None else 0,
+                                                L.ptr(z), L.ptr(pts), int(out_ch), L.ptr(packed), L.ptr(raw),
+                                                L.ptr(acts), L.ptr(masks), L.stream()), "nerfb_mlp_fwd_save_nv_bf16")
+    _count()
+    return raw
+
+
+def mlp_bwd_chain_nv_bf16(nrows, d_raw, d_raw4, packed_bwd, masks, gstore):
+    L.check(L.load().nerfb_mlp_bwd_chain_nv_bf16(int(nrows), L.ptr(d_raw), L.ptr(d_raw4), L.ptr(packed_bwd),
+                                                 L.ptr(masks), L.ptr(gstore), L.stream()), "nerfb_mlp_bwd_chain_nv_bf16")
+    _count()
+
+
+def mlp_wgrad_nv_bf16(nrows, out_ch, acts, gstore, d_raw_padded, d_raw4_padded, grad_ptrs: Sequence[Optional[int]]):
+    arr = (C.c_void_p * L.NERFB_NUM_PARAMS)(*[p if p else None for p in grad_ptrs])
+    L.check(L.load().nerfb_mlp_wgrad_nv_bf16(int(nrows), int(out_ch), L.ptr(acts), L.ptr(gstore), L.ptr(d_raw_padded),
+                                             L.ptr(d_raw4_padded), arr, L.stream()), "nerfb_mlp_wgrad_nv_bf16")
+    _count()
+
+
 def umma_selftest(A, B, cta_group=1):
     N, K = B.shape
     assert A.shape == (128 * cta_group, K)

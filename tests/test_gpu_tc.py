@@ -376,3 +376,166 @@ def test_training_without_hierarchical_sampling_uses_tc_backward():
         if b.abs().max() > 0:
             c = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()
             assert c > 0.97, c
+
+
+# ------------------------------------------------ tensor-core backward, network WITHOUT view directions
+
+def _train_case_nv(R, S, out_ch, seed=6):
+    params = O.make_params(seed, use_viewdirs=False, input_ch_views=0, output_ch=out_ch)
+    gen = torch.Generator().manual_seed(seed)
+    K, c2w = O.blender_camera(64, 64, 50.0)
+    ro, rd = O.get_rays(64, 64, K, T(c2w))
+    idx = torch.randperm(64 * 64, generator=gen)[:R]
+    rays, _ = O.pack_rays(ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx], 2.0, 6.0, use_viewdirs=False)
+    z = (torch.rand(R, S, generator=gen) * 4 + 2).sort(-1)[0]
+    d_raw = torch.randn(R * S, out_ch, generator=gen) * torch.tensor([1.0, 1.0, 1.0, 0.3, 0.5][:out_ch])
+    return params, rays, z, d_raw
+
+
+@pytest.mark.parametrize("R,S,out_ch", [(37, 64, 4), (300, 192, 5)])
+def test_tc_backward_no_viewdirs_stages_teacher_forced(R, S, out_ch):
+    """use_viewdirs=False (output_linear head, nerf.py:50-55): (1) forward-with-save returns the plain forward's raw and
+    stores gamma(x), h0..h7 and the sign bits; (2) the chain's first stage d_h7 = (d_raw W_out) * [h7>0] and W7^T..W1^T,
+    each recomputed in fp64 from the kernel's own stored tensors; (3) weight gradients incl. output_linear (all out_ch
+    rows: channel 4 of an out_ch=5 head gets its own gradient) from the stored tensors."""
+    from nerf_projects_b200 import mlp, ops, _lib
+    params, rays, z, d_raw = _train_case_nv(R, S, out_ch)
+    net = _net(params, False, out_ch)
+    n = R * S
+    rows, ntiles = _tile_rows(n)
+    valid = rows < n
+    rows_v = rows[valid].to(DEV)
+    FT, BT = ops.train_store_bytes(512, 0) // 4, ops.train_store_bytes(512, 1) // 4
+    PAN = 16384
+    try:
+        raw, (acts, masks) = mlp.forward_save_bf16(net, R, S, rays.to(DEV), z.to(DEV))
+        raw_plain = mlp.forward_bf16(net, R, S, rays.to(DEV), z.to(DEV))
+        torch.cuda.synchronize()
+        assert raw.shape == (n, out_ch) and torch.equal(raw, raw_plain), "forward-with-save changed the forward result"
+        gstore = torch.zeros(ops.train_store_bytes(n, 1), dtype=torch.uint8, device=DEV)
+        d_pad, d4 = mlp._padded_d_raw(net, d_raw.to(DEV), n, DEV)
+        assert (d4 is None) == (out_ch == 4)
+        ops.mlp_bwd_chain_nv_bf16(n, d_pad, d4, mlp.packed_weights_bwd(net), masks, gstore)
+        grads = mlp._zero_grads(net)
+        ops.mlp_wgrad_nv_bf16(n, out_ch, acts, gstore, d_pad, d4, mlp._param_ptrs(grads))
+        torch.cuda.synchronize()
+    except Exception:
+        print("watchdog:", _lib.watchdog_record())
+        raise
+
+    def panels(buf, tb, off, npan, check_pad=False):
+        full = _read_panels(buf, tb, ntiles, off, npan)
+        if check_pad and (~valid).any():
+            assert full[~valid.to(DEV)].abs().max().item() == 0      # padded rows carry zero gradient
+        out = torch.empty(n, full.shape[1], device=DEV)
+        out[rows_v] = full[valid.to(DEV)]
+        return out.cpu().double()
+
+    P = {k: v.double() for k, v in O.to_torch(params).items()}
+    bw = lambda t: bf16r(t.float()).double()
+    gx_s = panels(acts, FT, 0, 1)
+    h_s = [panels(acts, FT, PAN * (1 + 4 * l), 4) for l in range(8)]
+    dY_s = [panels(gstore, BT, PAN * (6 + 4 * l), 4, check_pad=True) for l in range(8)]
+    # forward store vs the oracle's fp32 activations
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3)
+    h = gx = O.embed(pts, 10)
+    tp = O.to_torch(params)
+    for l in range(8):
+        h = torch.relu(torch.nn.functional.linear(h, tp[f"pts_linears.{l}.weight"], tp[f"pts_linears.{l}.bias"]))
+        assert _rel(h_s[l].float(), h) < 2e-2, l
+        if l == 4:
+            h = torch.cat([gx, h], -1)
+    assert (gx_s[:, :63].float() - gx).abs().max().item() < 8e-3
+    # chain, teacher-forced
+    dr = d_raw.double()
+    terr = {"dY7": _rel(dY_s[7], (dr @ P["output_linear.weight"]) * (h_s[7] > 0))}
+    for l in range(7, 0, -1):
+        off = 63 if l == 5 else 0
+        terr[f"dY{l - 1}"] = _rel(dY_s[l - 1], (dY_s[l] @ bw(P[f"pts_linears.{l}.weight"][:, off:off + 256])) * (h_s[l - 1] > 0))
+    print("chain (teacher-forced) errors:", {k: f"{v:.2e}" for k, v in terr.items()})
+    assert all(v < 4e-3 for v in terr.values()), terr
+    # weight gradients, teacher-forced
+    X = [gx_s[:, :63]] + [h_s[l] for l in range(4)] + [torch.cat([gx_s[:, :63], h_s[4]], -1)] + [h_s[5], h_s[6]]
+    want = {}
+    for l in range(8):
+        want[f"pts_linears.{l}.weight"], want[f"pts_linears.{l}.bias"] = dY_s[l].T @ X[l], dY_s[l].sum(0)
+    want["output_linear.weight"], want["output_linear.bias"] = dr.T @ h_s[7], dr.sum(0)
+    werr = {k: _rel(grads[k].cpu().double(), want[k]) for k in want}
+    print("weight gradients (teacher-forced):", {k: f"{v:.1e}" for k, v in werr.items()})
+    assert all(v < 1e-4 for v in werr.values()), werr
+    assert grads["views_linears.0.weight"].abs().max().item() == 0      # exists in the state_dict, never used (nerf.py:41)
+
+
+@pytest.mark.parametrize("R,S,out_ch", [(2000, 192, 5), (1, 64, 4), (3, 192, 5), (700, 64, 4)])
+def test_tc_backward_no_viewdirs_matches_fp32_kernels(R, S, out_ch):
+    """mlp.backward (bf16 mode -> tensor cores) against the fp32 CUDA-core backward: several chunks / many tiles per CTA,
+    one ray, ragged sizes; run-to-run stability."""
+    from nerf_projects_b200 import mlp, _lib
+    params, rays, z, d_raw = _train_case_nv(R, S, out_ch, seed=10 + out_ch)
+    net = _net(params, False, out_ch)
+    assert mlp.supports_bf16_backward(net)
+    rays, z, d_raw = rays.to(DEV), z.to(DEV), d_raw.to(DEV)
+    old = mlp.TRAIN_ROWS_PER_CHUNK
+    mlp.TRAIN_ROWS_PER_CHUNK = 100000
+    try:
+        g_tc = mlp.backward(net, R, S, rays, z, None, None, d_raw)
+        g_tc2 = mlp.backward_bf16(net, R, S, rays, z, None, None, d_raw)
+        torch.cuda.synchronize()
+    except Exception:
+        print("watchdog:", _lib.watchdog_record())
+        raise
+    finally:
+        mlp.TRAIN_ROWS_PER_CHUNK = old
+    g_ref = mlp.backward_fp32(net, R, S, rays, z, None, None, d_raw)
+    used = [k for k in g_ref if float(g_ref[k].abs().max()) > 0]
+    assert "output_linear.weight" in used and "pts_linears.0.weight" in used
+    cos = {k: torch.nn.functional.cosine_similarity(g_tc[k].flatten(), g_ref[k].flatten(), dim=0).item() for k in used}
+    print("cosine:", {k: f"{v:.4f}" for k, v in cos.items()})
+    assert all(v > 0.97 for v in cos.values()), cos
+    assert all(torch.isfinite(v).all() for v in g_tc.values())
+    assert all(_rel(g_tc[k], g_tc2[k]) < 1e-4 for k in used)
+
+
+def test_training_no_viewdirs_through_render_uses_tc_backward():
+    """BASELINE config C0's model (no view directions, 64 samples) and a 40+24 hierarchical variant through render() +
+    loss.backward(): bf16 mode (forward-with-save + tensor-core backward) vs fp32 validation mode."""
+    import types, tempfile
+    import nerf_projects_b200 as nb
+    from nerf_projects_b200 import mlp
+    for N_samples, N_imp in ((64, 0), (40, 24)):
+        args = types.SimpleNamespace(multires=10, i_embed=0, use_viewdirs=False, multires_views=4, N_importance=N_imp,
+                                     netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536,
+                                     lrate=5e-4, basedir=tempfile.mkdtemp(prefix="nerfb_"), expname="t", ft_path=None,
+                                     no_reload=True, perturb=0.0, N_samples=N_samples, white_bkgd=True, raw_noise_std=0.0,
+                                     dataset_type="blender", no_ndc=False, lindisp=False)
+        kw_train, kw_test, start, grad_vars, optim = nb.create_nerf(args)
+        # calibrated scenes of the golden cases (plain random init renders empty space: zero gradients)
+        from _cases import case_params
+        pc, pf = case_params("render_nov_40_24" if N_imp > 0 else "render_c0_scene")
+        kw_train["network_fn"].load_state_dict(O.to_torch(pc))
+        if N_imp > 0:
+            kw_train["network_fine"].load_state_dict(O.to_torch(pf))
+        assert mlp.can_save_forward(kw_train["network_fn"], 1024 * N_samples)
+        K, c2w = O.blender_camera(32, 32, 20.0)
+        ro, rd = O.get_rays(32, 32, K, T(c2w))
+        rays = (ro.reshape(-1, 3).to(DEV), rd.reshape(-1, 3).to(DEV))
+        target = torch.rand(32 * 32, 3, generator=torch.Generator().manual_seed(0)).to(DEV)
+        kw = dict(kw_train); kw.update(ndc=False, lindisp=False)
+        grads = {}
+        for prec in ("bf16", "fp32"):
+            nb.set_precision(prec)
+            try:
+                optim.zero_grad()
+                rgb, disp, acc, extras = nb.render(32, 32, K, rays=rays, near=2., far=6., **kw)
+                loss = nb.img2mse(rgb, target) + (nb.img2mse(extras["rgb0"], target) if N_imp > 0 else 0.0)
+                loss.backward()
+                grads[prec] = [None if p.grad is None else p.grad.detach().clone() for p in grad_vars]
+            finally:
+                nb.set_precision("bf16")
+        n_checked = 0
+        for a, b in zip(grads["bf16"], grads["fp32"]):
+            if b is not None and b.abs().max() > 0:
+                c = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()
+                assert c > 0.95, c
+                n_checked += 1
+        assert n_checked >= 18 * (2 if N_imp > 0 else 1), n_checked

@@ -23,7 +23,7 @@ def schedule(which):
     return L, O, nlay.value, ring.value
 
 
-@pytest.mark.parametrize("which,nlayers,nloads", [(0, 10, 41), (1, 8, 31), (2, 9, 34)])
+@pytest.mark.parametrize("which,nlayers,nloads", [(0, 10, 41), (1, 8, 31), (2, 9, 34), (3, 7, 28)])
 def test_schedule_invariants(which, nlayers, nloads):
     loads, ops, nlay, ring = schedule(which)
     assert nlay == nlayers and len(loads) == nloads and ring >= 4
