@@ -349,6 +349,8 @@ static int launch_wgrad(const char* who, long long nrows, int use_viewdirs, int 
   int narrow_w = 50, views_w = 9 * 8 + 1;   // (measured sweep: profiles/README.md)
   if (const char* e = getenv("NERFB_WG_NARROW_W")) narrow_w = atoi(e);
   if (const char* e = getenv("NERFB_WG_VIEWS_W")) views_w = atoi(e);
+  int out_w = 110;                          // output_linear job: 33 KB per stage but 5 CUDA-core FMAs per staged element (sweep: profiles/README.md)
+  if (const char* e = getenv("NERFB_WG_OUT_W")) out_w = atoi(e);
   auto plain = [&](uint32_t a_off, uint32_t b_off, float* dW, int ld, int col_off, float* dbias) {
     WJob j{};
     j.a_off = a_off; j.a_panels = 4;
@@ -382,7 +384,7 @@ static int launch_wgrad(const char* who, long long nrows, int use_viewdirs, int 
     j.x_off = hL + 7 * 4 * kPanel; j.x_panels = 4;
     j.simt = SIMT_OUT;
     j.head_w = G(NERFB_P_OUTPUT_W); j.head_b = G(NERFB_P_OUTPUT_B);
-    j.weight = narrow_w;
+    j.weight = out_w;
     a.jobs[n++] = j;
   }
   if (use_viewdirs) {  // feature_linear (+ alpha_linear on CUDA cores from the same h7 tiles)

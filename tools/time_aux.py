@@ -1,0 +1,38 @@
+"""CUDA-event timing of the small kernels beside the MLP (GPU box only): keyed random draws of one training step, the fused
+SSIM/MSE/PSNR pass on an 800x800 frame, against their algorithmic bytes."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nerf_projects_b200 as nb  # noqa: E402
+from nerf_projects_b200 import metrics, rng  # noqa: E402
+
+dev = "cuda"
+
+
+def timeit(fn, reps=50):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3      # us
+
+
+for R in (4096, 32768):
+    with nb.keyed_rng(1):
+        us = timeit(lambda: rng.render_rays_draws(R, 64, 128, True, 1.0, dev))
+    nbytes = R * (64 + 128 + 64 + 192) * 4
+    us_t = timeit(lambda: (torch.rand((R, 64), device=dev), torch.rand((R, 128), device=dev),
+                           torch.randn((R, 64), device=dev) * 1.0, torch.randn((R, 192), device=dev) * 1.0))
+    print(f"keyed draws R={R}: {us:7.1f} us  ({nbytes / us / 1e3:7.1f} GB/s written)   torch.rand/randn x4: {us_t:7.1f} us")
+for H, W in ((800, 800), (756, 1008)):
+    a, b = torch.rand(H, W, 3, device=dev), torch.rand(H, W, 3, device=dev)
+    us = timeit(lambda: metrics.image_metrics(a, b))
+    print(f"image_metrics {H}x{W}: {us:7.1f} us  ({H * W * 3 * 8 / us / 1e3:7.1f} GB/s algorithmic read)")

@@ -1,6 +1,6 @@
 """Per-kernel CUDA-event timing of one training step's MLP backward (GPU box only).
 
-    python tools/time_train.py [rays] [reps]
+    python tools/time_train.py [rays] [reps] [nv]       (nv: the network without view directions, out_ch 5)
 Prints ms and achieved TFLOP/s / GB/s of: fused forward, forward-with-save, data-gradient chain,
 weight-gradient kernel on a [rays x 192] fine-network batch."""
 import os
@@ -43,6 +43,25 @@ legs = {
                   9 * 32 + 38 * 128 + 16),
     "wgrad": (lambda: ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs), 1186816, 10.4 * 1024),
 }
+if len(sys.argv) > 3 and sys.argv[3] == "nv":
+    # network without view directions: output_linear head (492 544 MACs forward, 7 chain layers, 33 + 32 stored panels)
+    net = nb.NeRF(8, 256, 63, 0, 5, [4], False).to(dev)
+    net.load_state_dict(SY.random_init_state_dict(1, use_viewdirs=False, input_ch_views=0, output_ch=5))
+    packed, packed_bwd = mlp.packed_weights(net), mlp.packed_weights_bwd(net)
+    raw5 = torch.empty(n, 5, device=dev)
+    d4 = torch.zeros(npad, device=dev)
+    gptrs_nv = mlp._param_ptrs(mlp._zero_grads(net))
+    rays8 = rays[:, :8].contiguous()
+    fl = 2 * (63 * 256 + 4 * 65536 + 319 * 256 + 2 * 65536 + 256 * 5)
+    legs = {
+        "fwd": (lambda: ops._mlp_fwd_bf16(R, S, rays8, z, None, None, False, 5, packed, raw5), fl, 24),
+        "fwd_save": (lambda: ops.mlp_fwd_save_nv_bf16(R, S, rays8, z, None, 5, packed, raw5, acts, masks), fl,
+                     33 * 128 + 8 * 32 + 24),
+        "bwd_chain": (lambda: ops.mlp_bwd_chain_nv_bf16(n, d_pad, d4, packed_bwd, masks, gstore), 2 * 7 * 65536,
+                      8 * 32 + 32 * 128 + 20),
+        "wgrad": (lambda: ops.mlp_wgrad_nv_bf16(n, 5, acts, gstore, d_pad, d4, gptrs_nv), fl,
+                  (32 + 4 * 7 + 2 + 4) * 128 + 20),
+    }
 for name, (fn, flop, bytes_per_row) in legs.items():
     for _ in range(2):
         fn()
