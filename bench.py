@@ -280,15 +280,19 @@ def main():
         target = torch.rand((n_batch, 3), device=dev, generator=gen)
         bucket = parallel.GradBucket(grad_vars)
 
+        tr_count = [0]
+
         def step_train():
+            # perturb / noise draws keyed by (seed, step, global ray index): the step does not depend on the number of GPUs
+            tr_count[0] += 1
             parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, H, W, K, b_o, b_d, target,
-                                        chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
+                                        rng_seed=nb.step_seed(0, tr_count[0]), chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
         for _ in range(3):
             step_train()
         tr_steps = 5
         tr_ms = timed(step_train, tr_steps)
         train = {"value": n_batch * tr_steps / (tr_ms * 1e-3), "unit": "rays/s", "ms_per_step": tr_ms / tr_steps,
-                 "config": f"{n_batch}-ray batch, 64+128, perturb=1, raw_noise_std=1, MSE(rgb)+MSE(rgb0), Adam; "
+                 "config": f"{n_batch}-ray batch, 64+128, perturb=1, raw_noise_std=1 (keyed Philox draws), MSE(rgb)+MSE(rgb0), Adam; "
                            "forward + backward on bf16 tensor cores (recompute-with-save, data-gradient chain, split-K weight gradients)"}
 
     rays_per_step = n_rays * world

@@ -300,6 +300,8 @@ def _padded_d_raw(net, d_raw, n, dev):
     npad = (n + 511) // 512 * 512
     ch = _raw_ch(net)
     d_raw = L.f32c(d_raw).view(-1, ch)
+    if ch == 4 and npad == n and d_raw.data_ptr() % 16 == 0:
+        return d_raw, None                 # whole super-tiles already (e.g. 4096 rays x 64 | 192 samples): no copy
     d_pad = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
     d_pad[:n].copy_(d_raw[:, :4])
     d4 = None

@@ -87,14 +87,16 @@ class GradBucket:
         """sum over ranks of d(sum-loss)/dp divided by world (the MSE is a mean over the
         global batch); gradients are written back into p.grad."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return                               # nothing to average: the gradients stay where backward() put them
+        have = [(v, p.grad) for p, v in zip(self.params, self.views) if p.grad is not None]
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
-                v.copy_(p.grad)
-        if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / world)
+        if have:                                 # one multi-tensor copy instead of one launch per parameter
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.mul_(1.0 / world)
         for p, v in zip(self.params, self.views):
             p.grad = v
 

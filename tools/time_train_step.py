@@ -15,8 +15,11 @@ sel = torch.randint(0, 640000, (4096,), device=dev, generator=gen)
 bo, bd = ro[sel].contiguous(), rd[sel].contiguous()
 target = torch.rand((4096, 3), device=dev, generator=gen)
 bucket = parallel.GradBucket(gv)
+cnt = [0]
 def step():
-    parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, 800, 800, K, bo, bd, target, chunk=32768, near=2., far=6., **kw)
+    cnt[0] += 1
+    parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, 800, 800, K, bo, bd, target,
+                                rng_seed=nb.step_seed(0, cnt[0]), chunk=32768, near=2., far=6., **kw)
 for _ in range(3): step()
 torch.cuda.synchronize()
 for rep in range(3):
