@@ -20,7 +20,7 @@ SOURCES = ["api.cu", "rays.cu", "embed.cu", "linear_fp32.cu", "composite.cu", "s
            "umma_selftest.cu", "mlp_tc.cu", "wgrad_tc.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", CSRC] + os.environ.get("NERFB_DEFINES", "").split()
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NERFB_DEFINES", "").split()
 
 
 def _nvcc() -> str:
@@ -34,7 +34,7 @@ def _stamp(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode()); h.update(f.read())
+            h.update(os.path.basename(p).encode()); h.update(f.read())     # content-addressed: independent of the checkout path
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
@@ -62,7 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj, stamp_file, stamp = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        # -I csrc: override sources (NERFB_SRC_OVERRIDE_DIR) live elsewhere but include the in-tree headers; the include
+        # path is not part of the stamp, so a checkout at another absolute path does not rebuild
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", CSRC, "-c", src, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = res.stdout + res.stderr
         with open(obj + ".log", "w") as f:

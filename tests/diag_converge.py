@@ -1,6 +1,7 @@
 """Diagnostic (GPU box only): the end-to-end training loop of tests/test_gpu_render.py::test_end_to_end_training_converges_bf16
 as a script, optionally after polluting the caching allocator with NaN / huge values, to tell numerical chaos from reads of
-uninitialised memory.   python tools/converge_probe.py [none|nan|big] [steps] [seed]"""
+uninitialised memory.  Lives under tests/ (not collected by pytest) because it builds its teacher scene with the oracle.
+    INIT_SEED=k python tests/diag_converge.py [none|nan|big] [steps] [seed]"""
 import os
 import sys
 import tempfile
@@ -11,7 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))    # _cases
 import nerf_projects_b200 as nb  # noqa: E402
 from oracle import nerf_oracle as O  # noqa: E402
 from _cases import T, case_params  # noqa: E402

@@ -532,7 +532,7 @@ def test_end_to_end_training_converges_bf16():
     assert float(images.std()) > 0.02, "teacher scene is flat"
     args = make_args(True, 128)
     # the student's initialisation decides whether 300 steps leave the all-background plateau (loss ~0.15) that NeRF on a
-    # white background is known for (the reference uses precrop_iters against it): measured with tools/converge_probe.py,
+    # white background is known for (the reference uses precrop_iters against it): measured with tests/diag_converge.py,
     # seeds 0-3 converge to ~0.003, seeds 4-7 stay at 0.15 -- with the reference algorithm, not a property of the kernels.
     # The seed must be set BEFORE create_nerf (nn.Linear default init draws from the CPU generator).
     torch.manual_seed(0)
