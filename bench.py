@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step leg")
+    ap.add_argument("--no-llff", action="store_true", help="skip the extra LLFF-shaped (NDC) render leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -268,6 +269,30 @@ def main():
         step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
 
+    # ---- extra leg: LLFF-shaped forward-facing frames (BASELINE configs[3]: 1008x756, NDC, near 0 / far 1, no white
+    # background), N frames per step each ray-sharded over the N ranks, rays resident in HBM
+    llff = None
+    if not args.no_llff:
+        Hl, Wl = 756, 1008
+        Kl, c2wl = SY.llff_shaped_camera(Hl, Wl)
+        ro_l, rd_l = nb.get_rays(Hl, Wl, Kl, torch.from_numpy(c2wl).to(dev))
+        ro_l, rd_l = ro_l.reshape(-1, 3), rd_l.reshape(-1, 3)
+        kw_l = dict(kw_test); kw_l.update(ndc=True, white_bkgd=False, lindisp=False)
+
+        def step_llff():
+            for _ in range(world):
+                if world == 1:
+                    nb.render(Hl, Wl, Kl, chunk=args.chunk, rays=(ro_l, rd_l), near=0., far=1., **kw_l)
+                else:
+                    parallel.render_sharded(nb.render, Hl, Wl, Kl, ro_l, rd_l, chunk=args.chunk, near=0., far=1., **kw_l)
+        with torch.no_grad():
+            step_llff()
+            ll_steps = 3
+            ll_ms = timed(step_llff, ll_steps)
+        llff = {"value": Hl * Wl * world * ll_steps / (ll_ms * 1e-3), "unit": "rays/s", "ms_per_step": ll_ms / ll_steps,
+                "config": f"C3: {Wl}x{Hl} LLFF-shaped NDC frame(s), coarse 64 + fine 128, use_viewdirs, "
+                          f"{'ray-sharded x' + str(world) if world > 1 else 'single GPU'}"}
+
     # ---- extra leg: one optimisation step of train() on a 4096-ray batch per GPU (BASELINE configs[2]/[4]):
     # fused forward + backward through the kernels + fused Adam, data-parallel all-reduce when world > 1
     train = None
@@ -328,6 +353,8 @@ def main():
         }
         if train is not None:
             line["train"] = train
+        if llff is not None:
+            line["llff"] = llff
         if world == 1 and not args.no_cpu_baseline:
             n = 8192
             rate, dt, cores = cpu_reference_rate(n, 2, 1)
