@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nerf_projects_b200 as nb  # noqa: E402
-from nerf_projects_b200 import metrics, rng  # noqa: E402
+from nerf_projects_b200 import metrics, ops, rng  # noqa: E402
 
 dev = "cuda"
 
@@ -36,3 +36,18 @@ for H, W in ((800, 800), (756, 1008)):
     a, b = torch.rand(H, W, 3, device=dev), torch.rand(H, W, 3, device=dev)
     us = timeit(lambda: metrics.image_metrics(a, b))
     print(f"image_metrics {H}x{W}: {us:7.1f} us  ({H * W * 3 * 8 / us / 1e3:7.1f} GB/s algorithmic read)")
+
+# compositing: one 32768-ray chunk, coarse (64) and fine (192) sample counts; algorithmic bytes = raw + z in (+ weights out),
+# backward = raw + z + noise in, d_raw out
+R = 32768
+for S in (64, 192):
+    raw = torch.randn(R, S, 4, device=dev)
+    z = (torch.rand(R, S, device=dev) * 4 + 2).sort(-1)[0]
+    d = torch.nn.functional.normalize(torch.randn(R, 3, device=dev), dim=-1)
+    noise = torch.randn(R, S, device=dev)
+    g = torch.randn(R, 3, device=dev)
+    us_f = timeit(lambda: ops.raw2outputs_fwd(raw, z, d, None, True, want_weights=(S == 64)), 30)
+    us_b = timeit(lambda: ops.raw2outputs_bwd(raw, z, d, noise, True, g, None, None, None, None), 30)
+    bf = R * S * (16 + 4 + (4 if S == 64 else 0))
+    bb = R * S * (16 + 4 + 4 + 16)
+    print(f"raw2outputs S={S}: fwd {us_f:6.1f} us ({bf / us_f / 1e6:5.2f} TB/s)   bwd {us_b:6.1f} us ({bb / us_b / 1e6:5.2f} TB/s)")
