@@ -87,3 +87,18 @@ def test_product_does_not_import_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle|from\s+oracle|import_module\(.oracle", src, re.M), \
                 f"{fn} imports the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/nerf_b200.h is the C ABI: it must compile as C99 (and as C++) on its own -- no torch / CUDA types."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "nerf_b200.h"\nint main(void) { return nerfb_abi_version() == NERFB_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"],
+                ["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++"]):
+        res = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
