@@ -25,7 +25,7 @@ from .data import RayBatcher, precrop_pixel_ids  # noqa: F401
 from .metrics import calculate_lpips, calculate_metrics, calculate_ssim  # noqa: F401
 from .rng import keyed_rng, step_seed  # noqa: F401
 from .datasets import load_blender_data, load_llff_data, pose_spherical  # noqa: F401
-from .train import train  # noqa: F401
+from .trainer import train  # noqa: F401
 from . import ops  # noqa: F401
 
 __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network", "batchify", "raw2outputs",
