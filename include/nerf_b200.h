@@ -154,6 +154,14 @@ int nerfb_hierarchical_z(int R, int S, int N, const float* z, const float* weigh
                          int det, const float* u, float* z_out, float* z_samples,
                          long long* inds, float* z_std, void* stream);
 
+/* Coarse compositing + hierarchical resampling in one launch (render_rays, ipynb:451-467): raw2outputs of the coarse
+ * pass (rgb/disp/acc/depth = the reference's rgb0/disp0/acc0 + depth0), then nerfb_hierarchical_z on its weights, which
+ * stay in shared memory (written to `weights` [R,S] only when not NULL).  Bit-identical to the two separate calls. */
+int nerfb_composite_resample(int R, int S, int N, const float* raw, int raw_ch, const float* z,
+                             const float* rays_d, int ld_d, const float* noise, int white_bkgd, int det,
+                             const float* u, float* rgb, float* disp, float* acc, float* depth,
+                             float* weights, float* z_out, float* z_samples, float* z_std, void* stream);
+
 /* ------------------------------------------- fused tensor-core MLP (bf16) */
 
 /* Canonical NeRF MLP only: D=8, W=256, skips=[4], multires 10 (63 ch),

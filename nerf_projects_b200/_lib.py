@@ -39,6 +39,8 @@ _SIGS = {
     "nerfb_raw2outputs_bwd": ([_i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_sample_pdf": ([_i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_hierarchical_z": ([_i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_composite_resample": ([_i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp], _i),
     "nerfb_packed_weights_bytes": ([_i], C.c_size_t),
     "nerfb_pack_weights": ([C.POINTER(_vp), _i, _i, _vp, _vp], _i),
     "nerfb_mlp_fwd_bf16": ([_i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),

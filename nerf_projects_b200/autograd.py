@@ -77,7 +77,7 @@ class RenderRaysFn(Function):
     recomputes the MLP activations chunk by chunk.
 
     apply(cfg, rays, t_rand, u, noise_c, noise_f, n_coarse_params, *params)
-    returns (rgb, disp, acc, depth, weights, raw, z_vals,
+    returns (rgb, disp, acc, depth, <empty: final weights are not materialised>, raw, z_vals,
              rgb0, disp0, acc0, depth0, z_std, z_samples)
     """
 
@@ -102,29 +102,33 @@ class RenderRaysFn(Function):
             raw_c = raw_c.view(R, S, -1)
         else:
             raw_c = mlp.forward(net_c, R, S, rays, z_c).view(R, S, -1)
-        need_w = N_imp > 0
-        rgb, disp, acc, weights, depth = ops.raw2outputs_fwd(raw_c, z_c, rays_d, noise_c, white, want_weights=True)
         ctx.cfg = cfg
         ctx.R = R
         empty = rays.new_empty(0)
         if N_imp > 0:
+            # coarse compositing + z_mid / sample_pdf / sort / z_std in one launch: the coarse weights stay on-chip
             det = (t_rand is None and u is None)
-            z_f, z_samples, z_std, _ = ops.hierarchical_z(z_c, weights, N_imp, det, u)
+            rgb, disp, acc, depth, _, z_f, z_samples, z_std = ops.composite_resample(raw_c, z_c, rays_d, noise_c, white,
+                                                                                     N_imp, det, u)
+        else:
+            # (the per-sample weights of the final pass are not part of render_rays' result: not written to HBM)
+            rgb, disp, acc, _, depth = ops.raw2outputs_fwd(raw_c, z_c, rays_d, noise_c, white, want_weights=False)
+        if N_imp > 0:
             run = net_f if net_f is not None else net_c
             if train_f and mlp.can_save_forward(run, R * (S + N_imp)):
                 raw_f, ctx.acts_f = mlp.forward_save_bf16(run, R, S + N_imp, rays, z_f)
                 raw_f = raw_f.view(R, S + N_imp, -1)
             else:
                 raw_f = mlp.forward(run, R, S + N_imp, rays, z_f).view(R, S + N_imp, -1)
-            rgb_f, disp_f, acc_f, weights_f, depth_f = ops.raw2outputs_fwd(raw_f, z_f, rays_d, noise_f, white)
+            rgb_f, disp_f, acc_f, _, depth_f = ops.raw2outputs_fwd(raw_f, z_f, rays_d, noise_f, white, want_weights=False)
             ctx.save_for_backward(rays, z_c, raw_c, z_f, raw_f, noise_c if noise_c is not None else empty,
                                   noise_f if noise_f is not None else empty)
-            outs = (rgb_f, disp_f, acc_f, depth_f, weights_f, raw_f, z_f, rgb, disp, acc, depth, z_std, z_samples)
-            ctx.mark_non_differentiable(weights_f, z_f, z_std, z_samples)
+            outs = (rgb_f, disp_f, acc_f, depth_f, empty, raw_f, z_f, rgb, disp, acc, depth, z_std, z_samples)
+            ctx.mark_non_differentiable(z_f, z_std, z_samples)
         else:
             ctx.save_for_backward(rays, z_c, raw_c, empty, empty, noise_c if noise_c is not None else empty, empty)
-            outs = (rgb, disp, acc, depth, weights, raw_c, z_c, empty, empty, empty, empty, empty, empty)
-            ctx.mark_non_differentiable(weights, z_c)
+            outs = (rgb, disp, acc, depth, empty, raw_c, z_c, empty, empty, empty, empty, empty, empty)
+            ctx.mark_non_differentiable(z_c)
         return outs
 
     @staticmethod

@@ -9,7 +9,7 @@
 //     (all partial sums are exact in fp64, so a parallel scan is bit-safe);
 //   * u = torch.linspace formula (single-rounded fma in the upper half);
 //   * searchsorted(right=True) by binary search; un-fused fp32 lerp.
-#include "common.cuh"
+#include "composite.cuh"
 #include <math_constants.h>
 
 namespace nerfb {
@@ -143,21 +143,16 @@ sample_pdf_kernel(int R, int M, int N, const float* __restrict__ bins, int ld_bi
   }
 }
 
-__global__ void __launch_bounds__(32 * PW)
-hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, const float* __restrict__ weights,
-                      int det, const float* __restrict__ u_in, float* __restrict__ z_out,
-                      float* __restrict__ z_samples, long long* __restrict__ inds, float* __restrict__ z_std) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int r = blockIdx.x * PW + wib;
-  if (r >= R) return;
+// The z_mid / sample_pdf / sort / z_std block of render_rays for ONE ray (one warp).  `wr` = the ray's S compositing
+// weights (global OR shared memory: the fused kernel below keeps them on-chip), `s_base` = 3*(S-1) + P floats of scratch.
+__device__ void hierarchical_z_ray(int S, int N, int P, const float* zr, const float* wr, int det, const float* u_row,
+                                   float* z_out_row, float* z_samples_row, long long* inds_row, float* z_std,
+                                   float* s_base, int lane) {
   const int M = S - 1;  // bins = z_mid (S-1 edges), weights[1:-1] (S-2 values)
-  float* s_w = smem + (size_t)wib * (3 * M + P);
+  float* s_w = s_base;
   float* s_cdf = s_w + M;
   float* s_bins = s_cdf + M;
   float* s_sort = s_bins + M;
-  const float* zr = z + (size_t)r * S;
-  const float* wr = weights + (size_t)r * S;
   for (int j = lane; j < M - 1; j += 32) s_w[j] = __fadd_rn(wr[j + 1], 1e-5f);
   for (int j = lane; j < M; j += 32) s_bins[j] = __fmul_rn(0.5f, __fadd_rn(zr[j + 1], zr[j]));
   for (int j = lane; j < S; j += 32) s_sort[j] = zr[j];
@@ -166,13 +161,13 @@ hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, c
   build_cdf(s_w, s_cdf, M, lane);
   double sum = 0.0;
   for (int i = lane; i < N; i += 32) {
-    const float u = det ? linspace01(i, N) : u_in[(size_t)r * N + i];
+    const float u = det ? linspace01(i, N) : u_row[i];
     int ind;
     const float s = draw_sample(s_cdf, s_bins, M, u, &ind);
     s_sort[S + i] = s;
     sum += (double)s;
-    if (z_samples) z_samples[(size_t)r * N + i] = s;
-    if (inds) inds[(size_t)r * N + i] = ind;
+    if (z_samples_row) z_samples_row[i] = s;
+    if (inds_row) inds_row[i] = ind;
   }
   __syncwarp();
   if (z_std) {  // torch.std(unbiased=False): population std of the N new samples
@@ -186,7 +181,7 @@ hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, c
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    if (lane == 0) z_std[r] = (float)sqrt(var / N);
+    if (lane == 0) *z_std = (float)sqrt(var / N);
   }
   // torch.sort(cat([z_vals, z_samples])) returns values only, so any correct sort is bit-identical.  When both lists
   // are already non-decreasing (always for the coarse depths; for the new samples whenever u is sorted, i.e. the
@@ -207,7 +202,7 @@ hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, c
       if (A[mid] <= B[p0 - mid - 1]) lo = mid + 1; else hi = mid;
     }
     int i = lo, j = p0 - lo;
-    float* out = z_out + (size_t)r * T;
+    float* out = z_out_row;
     for (int p = p0; p < p1; ++p) {
       const bool take_a = (i < S) && (j >= N || A[i] <= B[j]);
       out[p] = take_a ? A[i] : B[j];
@@ -229,7 +224,68 @@ hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, c
       __syncwarp();
     }
   }
-  for (int j = lane; j < S + N; j += 32) z_out[(size_t)r * (S + N) + j] = s_sort[j];
+  for (int j = lane; j < S + N; j += 32) z_out_row[j] = s_sort[j];
+}
+
+__global__ void __launch_bounds__(32 * PW)
+hierarchical_z_kernel(int R, int S, int N, int P, const float* __restrict__ z, const float* __restrict__ weights,
+                      int det, const float* __restrict__ u_in, float* __restrict__ z_out,
+                      float* __restrict__ z_samples, long long* __restrict__ inds, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * PW + wib;
+  if (r >= R) return;
+  hierarchical_z_ray(S, N, P, z + (size_t)r * S, weights + (size_t)r * S, det, u_in ? u_in + (size_t)r * N : nullptr,
+                     z_out + (size_t)r * (S + N), z_samples ? z_samples + (size_t)r * N : nullptr,
+                     inds ? inds + (size_t)r * N : nullptr, z_std ? z_std + r : nullptr,
+                     smem + (size_t)wib * (3 * (S - 1) + P), lane);
+}
+
+// Coarse compositing + hierarchical resampling of a ray in ONE kernel (ipynb:451-467): raw2outputs of the coarse pass
+// (rgb0 / disp0 / acc0 / depth0), then z_mid, sample_pdf(weights[1:-1]), sort(cat) and z_std with the S coarse weights
+// kept in shared memory -- they never go to HBM unless the caller asks for them (`weights` != NULL).  Same device
+// functions as the two separate kernels, so every output is bit-identical to raw2outputs_fwd + hierarchical_z.
+__global__ void __launch_bounds__(32 * PW)
+composite_resample_kernel(int R, int S, int N, int P, const float* __restrict__ raw, int ch, const float* __restrict__ z,
+                          const float* __restrict__ rays_d, int ld_d, const float* __restrict__ noise, int white, int det,
+                          const float* __restrict__ u_in, float* __restrict__ rgb, float* __restrict__ disp,
+                          float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
+                          float* __restrict__ z_out, float* __restrict__ z_samples, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * PW + wib;
+  if (r >= R) return;
+  float* s_wts = smem + (size_t)wib * (S + 3 * (S - 1) + P);
+  const float* rr = raw + (size_t)r * S * ch;
+  const float* zr = z + (size_t)r * S;
+  const float* nr = noise ? noise + (size_t)r * S : nullptr;
+  const float nrm = ray_norm(rays_d + (size_t)r * ld_d);
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, dsum = 0.f, asum = 0.f;
+  float* wr = weights ? weights + (size_t)r * S : nullptr;
+  scan_ray(S, rr, ch, zr, nrm, nr, lane, [&](int i, float alpha, float x, float T) {
+    const float w = __fmul_rn(alpha, T);
+    s_wts[i] = w;
+    if (wr) wr[i] = w;
+    c0 += w * sigmoidf_(rr[(size_t)i * ch + 0]);
+    c1 += w * sigmoidf_(rr[(size_t)i * ch + 1]);
+    c2 += w * sigmoidf_(rr[(size_t)i * ch + 2]);
+    dsum += w * zr[i];
+    asum += w;
+  });
+  c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dsum = warp_sum(dsum); asum = warp_sum(asum);
+  if (lane == 0) {
+    if (white) {
+      const float bg = __fsub_rn(1.0f, asum);
+      c0 += bg; c1 += bg; c2 += bg;
+    }
+    rgb[3 * r + 0] = c0; rgb[3 * r + 1] = c1; rgb[3 * r + 2] = c2;
+    if (depth) depth[r] = dsum;
+    if (acc) acc[r] = asum;
+    if (disp) disp[r] = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(dsum, fmaxf(1e-10f, asum)), 1e-10f));
+  }
+  __syncwarp();
+  hierarchical_z_ray(S, N, P, zr, s_wts, det, u_in ? u_in + (size_t)r * N : nullptr, z_out + (size_t)r * (S + N),
+                     z_samples ? z_samples + (size_t)r * N : nullptr, nullptr, z_std ? z_std + r : nullptr, s_wts + S, lane);
 }
 
 }  // namespace nerfb
@@ -264,4 +320,22 @@ extern "C" int nerfb_hierarchical_z(int R, int S, int N, const float* z, const f
   hierarchical_z_kernel<<<cdiv(R, PW), 32 * PW, smem, as_stream(stream)>>>(R, S, N, P, z, weights, det, u, z_out,
                                                                           z_samples, inds, z_std);
   return check_launch("hierarchical_z_kernel");
+}
+
+extern "C" int nerfb_composite_resample(int R, int S, int N, const float* raw, int raw_ch, const float* z,
+                                        const float* rays_d, int ld_d, const float* noise, int white_bkgd, int det,
+                                        const float* u, float* rgb, float* disp, float* acc, float* depth, float* weights,
+                                        float* z_out, float* z_samples, float* z_std, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S >= 3 && N >= 1 && raw && z && rays_d && rgb && z_out && raw_ch >= 4 && ld_d >= 3,
+                "nerfb_composite_resample: bad arguments (R=%d S=%d N=%d)", R, S, N);
+  NERFB_REQUIRE(det || u, "nerfb_composite_resample: det=0 needs u");
+  int P = 1;
+  while (P < S + N) P <<= 1;
+  const size_t smem = (size_t)PW * (S + 3 * (S - 1) + P) * sizeof(float);
+  NERFB_REQUIRE(smem <= 48 * 1024, "nerfb_composite_resample: S+N too large (%d+%d)", S, N);
+  if (R == 0) return NERFB_OK;
+  composite_resample_kernel<<<cdiv(R, PW), 32 * PW, smem, as_stream(stream)>>>(
+      R, S, N, P, raw, raw_ch, z, rays_d, ld_d, noise, white_bkgd, det, u, rgb, disp, acc, depth, weights, z_out, z_samples,
+      z_std);
+  return check_launch("composite_resample_kernel");
 }

@@ -225,6 +225,24 @@ def hierarchical_z(z, weights, N, det=True, u=None, want_inds=False):
     return z_out, z_samples, z_std, inds
 
 
+def composite_resample(raw, z, rays_d, noise, white_bkgd, N, det=True, u=None, want_weights=False):
+    """Coarse raw2outputs + hierarchical_z in one launch (coarse weights stay on-chip) ->
+    (rgb0, disp0, acc0, depth0, weights|None, z_out, z_samples, z_std)."""
+    R, S, ch = raw.shape
+    L.require_cuda(raw, z, rays_d, noise, u)
+    rgb, disp, acc, depth = _empty((R, 3), raw), _empty((R,), raw), _empty((R,), raw), _empty((R,), raw)
+    weights = _empty((R, S), raw) if want_weights else None
+    z_out, z_samples, z_std = _empty((R, S + N), raw), _empty((R, N), raw), _empty((R,), raw)
+    if u is not None:
+        u = L.f32c(u)
+    L.check(L.load().nerfb_composite_resample(R, S, int(N), L.ptr(raw), ch, L.ptr(z), L.ptr(rays_d), rays_d.stride(0),
+                                              L.ptr(noise), int(bool(white_bkgd)), int(bool(det)), L.ptr(u), L.ptr(rgb),
+                                              L.ptr(disp), L.ptr(acc), L.ptr(depth), L.ptr(weights), L.ptr(z_out),
+                                              L.ptr(z_samples), L.ptr(z_std), L.stream()), "nerfb_composite_resample")
+    _count()
+    return rgb, disp, acc, depth, weights, z_out, z_samples, z_std
+
+
 # ------------------------------------------------ tensor-core MLP (bf16)
 
 def packed_weights_bytes(use_viewdirs: bool) -> int:

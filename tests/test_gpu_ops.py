@@ -397,3 +397,30 @@ def test_image_metrics_vs_reference_golden_and_oracle():
         nb.calculate_ssim(a[None], b[None])
     with pytest.raises(nb.NerfB200Error):
         nb.calculate_ssim(a, b, filter_size=10)
+
+
+@pytest.mark.parametrize("S,N", [(64, 128), (40, 24), (7, 5)])
+def test_composite_resample_equals_separate_kernels(S, N):
+    """The fused coarse compositing + hierarchical resampling launch (coarse weights kept in shared memory) against
+    raw2outputs_fwd followed by hierarchical_z: every output bit-identical -- deterministic and random u, with and
+    without density noise / white background, ragged ray counts."""
+    from nerf_projects_b200 import ops
+    gen = torch.Generator().manual_seed(S * 1000 + N)
+    for R, det, white, with_noise in ((1, True, True, False), (333, True, False, False), (1030, False, True, True)):
+        raw = torch.randn(R, S, 4, generator=gen)
+        raw[..., 3] = raw[..., 3] * 4 - 0.5
+        raw[: R // 4, :, 3] = -1.0                                   # empty rays (uniform pdf branch)
+        z = (torch.rand(R, S, generator=gen) * 4 + 2).sort(-1)[0]
+        d = torch.randn(R, 3, generator=gen)
+        noise = torch.randn(R, S, generator=gen) if with_noise else None
+        u = None if det else torch.rand(R, N, generator=gen)
+        raw, z, d = raw.to(DEV), z.to(DEV), d.to(DEV)
+        noise = noise.to(DEV) if noise is not None else None
+        u = u.to(DEV) if u is not None else None
+        rgb, disp, acc, w, depth = ops.raw2outputs_fwd(raw, z, d, noise, white, want_weights=True)
+        z_out, z_s, z_std, _ = ops.hierarchical_z(z, w, N, det, u)
+        f = ops.composite_resample(raw, z, d, noise, white, N, det, u, want_weights=True)
+        for got, want, name in zip(f, (rgb, disp, acc, depth, w, z_out, z_s, z_std),
+                                   ("rgb", "disp", "acc", "depth", "weights", "z_out", "z_samples", "z_std")):
+            assert torch.equal(got, want), (name, R, det)
+        assert ops.composite_resample(raw, z, d, noise, white, N, det, u)[4] is None
