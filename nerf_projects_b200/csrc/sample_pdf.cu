@@ -188,10 +188,36 @@ __device__ void hierarchical_z_ray(int S, int N, int P, const float* zr, const f
   // deterministic test-time case, up to last-ulp effects at bin edges) a merge-path merge does it in ~100
   // instructions per lane; the check below keeps the general bitonic sort as the fallback, so the result never
   // depends on that assumption.
-  bool sorted_in = true;
+  bool a_sorted = true, b_sorted = true;
   for (int i = lane; i < S + N; i += 32)
-    if (i != 0 && i != S && s_sort[i] < s_sort[i - 1]) sorted_in = false;
-  if (__all_sync(0xffffffffu, sorted_in)) {
+    if (i != 0 && i != S && s_sort[i] < s_sort[i - 1]) { if (i < S) a_sorted = false; else b_sorted = false; }
+  a_sorted = __all_sync(0xffffffffu, a_sorted);
+  b_sorted = __all_sync(0xffffffffu, b_sorted);
+  // random u (training): only the N new samples are out of order -> bitonic sort of those (padded with the +inf already
+  // behind them to PN = pow2 >= N, when that fits the buffer), then the same merge: 112 instead of 288 compare-exchanges
+  // per lane at 64 + 128
+  if (a_sorted && !b_sorted) {
+    int PN = 1;
+    while (PN < N) PN <<= 1;
+    if (S + PN <= P) {
+      float* Bs = s_sort + S;
+      for (int k = 2; k <= PN; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = lane; t < PN; t += 32) {
+            const int partner = t ^ j;
+            if (partner > t) {
+              const float a = Bs[t], b = Bs[partner];
+              const bool up = ((t & k) == 0);
+              if ((a > b) == up) { Bs[t] = b; Bs[partner] = a; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      b_sorted = true;
+    }
+  }
+  if (a_sorted && b_sorted) {
     const float* A = s_sort;            // S coarse depths
     const float* B = s_sort + S;        // N new samples
     const int T = S + N, per = (T + 31) / 32;

@@ -51,3 +51,12 @@ for S in (64, 192):
     bf = R * S * (16 + 4 + (4 if S == 64 else 0))
     bb = R * S * (16 + 4 + 4 + 16)
     print(f"raw2outputs S={S}: fwd {us_f:6.1f} us ({bf / us_f / 1e6:5.2f} TB/s)   bwd {us_b:6.1f} us ({bb / us_b / 1e6:5.2f} TB/s)")
+
+# hierarchical resampling of one 32768-ray chunk: deterministic (merge path) and random u (sort of the new samples + merge)
+R, S, N = 32768, 64, 128
+z = (torch.rand(R, S, device=dev) * 4 + 2).sort(-1)[0]
+w = torch.rand(R, S, device=dev) ** 5
+u = torch.rand(R, N, device=dev)
+us_d = timeit(lambda: ops.hierarchical_z(z, w, N, True, None), 30)
+us_r = timeit(lambda: ops.hierarchical_z(z, w, N, False, u), 30)
+print(f"hierarchical_z 32768 x (64+128): deterministic {us_d:6.1f} us   random u {us_r:6.1f} us")
