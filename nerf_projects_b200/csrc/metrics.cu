@@ -5,6 +5,7 @@
 // moments (x, y, x^2, y^2, xy) along W into shared memory, then along H in registers, evaluates the SSIM formula,
 // and writes one (ssim, squared-error) partial per CTA; a second one-CTA kernel adds the partials in a fixed
 // order (deterministic means).  HBM-bound: 8 B read per pixel-channel (+4 B when the map is requested).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace nerfb {
@@ -114,6 +115,134 @@ __global__ void __launch_bounds__(kThreads) ssim_mse_kernel(int H, int W, int C,
   }
 }
 
+// Specialisation for a compile-time window (the reference's default 11 taps): 32x32 pixel tile, every thread produces FOUR
+// adjacent outputs per pass from a register window -- the row pass reads 4 aligned float4 per image instead of 4 x FS
+// scalars, the column pass FS+3 values per moment instead of 4 x FS -- about 4x fewer shared-memory instructions than the
+// generic kernel above (68 -> see profiles/README.md).  Same summation order per output, so the values are identical.
+template <int FS>
+__global__ void __launch_bounds__(kThreads) ssim_mse_fixed_kernel(int H, int W, int C, const float* __restrict__ a,
+                                                                  const float* __restrict__ b, SsimArgs p,
+                                                                  float* __restrict__ ssim_map,
+                                                                  double* __restrict__ partials) {
+  constexpr int TH = 32, HW = FS / 2, IH = TH + 2 * HW, IW = kTW + 2 * HW, IWP = (IW + 3) / 4 * 4, WIN = FS + 3;
+  static_assert(4 * (kTW / 4 - 1) + 16 <= IWP, "row window must stay inside the padded row");
+  extern __shared__ float smem[];
+  float* sa = smem;                   // [IH][IWP]
+  float* sb = sa + IH * IWP;          // [IH][IWP]
+  float* sh = sb + IH * IWP;          // [5][IH][kTW]
+  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * kTW, tid = threadIdx.x;
+  double acc_ssim = 0.0, acc_se = 0.0;
+  for (int c = 0; c < C; ++c) {
+    for (int i = tid; i < IH * IWP; i += kThreads) {
+      const int r = i / IWP, q = i - r * IWP, y = y0 + r - HW, x = x0 + q - HW;
+      float va = 0.f, vb = 0.f;
+      if (q < IW && y >= 0 && y < H && x >= 0 && x < W) {
+        const size_t o = ((size_t)y * W + x) * C + c;
+        va = a[o];
+        vb = b[o];
+        if (r >= HW && r < HW + TH && q >= HW && q < HW + kTW) {
+          const float d = fminf(fmaxf(va, 0.f), 1.f) - fminf(fmaxf(vb, 0.f), 1.f);
+          acc_se += (double)(d * d);
+        }
+        va = fminf(fmaxf(va, 0.f), p.max_val);
+        vb = fminf(fmaxf(vb, 0.f), p.max_val);
+      }
+      sa[i] = va;
+      sb[i] = vb;
+    }
+    __syncthreads();
+    // ---- blur along W: item = (row r, group g of 4 output columns)
+    for (int it = tid; it < IH * (kTW / 4); it += kThreads) {
+      const int r = it / (kTW / 4), g = it - r * (kTW / 4);
+      float u[16], v[16];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 fa = *reinterpret_cast<const float4*>(sa + r * IWP + 4 * g + 4 * k4);
+        const float4 fb = *reinterpret_cast<const float4*>(sb + r * IWP + 4 * g + 4 * k4);
+        u[4 * k4] = fa.x; u[4 * k4 + 1] = fa.y; u[4 * k4 + 2] = fa.z; u[4 * k4 + 3] = fa.w;
+        v[4 * k4] = fb.x; v[4 * k4 + 1] = fb.y; v[4 * k4 + 2] = fb.z; v[4 * k4 + 3] = fb.w;
+      }
+      float uu[WIN], vv[WIN], uv[WIN];
+#pragma unroll
+      for (int k = 0; k < WIN; ++k) { uu[k] = u[k] * u[k]; vv[k] = v[k] * v[k]; uv[k] = u[k] * v[k]; }
+      float m[5][4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        float m0 = 0.f, m1 = 0.f, m00 = 0.f, m11 = 0.f, m01 = 0.f;
+#pragma unroll
+        for (int k = 0; k < FS; ++k) {
+          const float w = p.filt[k];
+          m0 = fmaf(w, u[o + k], m0);
+          m1 = fmaf(w, v[o + k], m1);
+          m00 = fmaf(w, uu[o + k], m00);
+          m11 = fmaf(w, vv[o + k], m11);
+          m01 = fmaf(w, uv[o + k], m01);
+        }
+        m[0][o] = m0; m[1][o] = m1; m[2][o] = m00; m[3][o] = m11; m[4][o] = m01;
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        *reinterpret_cast<float4*>(sh + (j * IH + r) * kTW + 4 * g) = make_float4(m[j][0], m[j][1], m[j][2], m[j][3]);
+    }
+    __syncthreads();
+    // ---- blur along H + SSIM: item = (group rg of 4 output rows, column q)
+    for (int it = tid; it < (TH / 4) * kTW; it += kThreads) {
+      const int rg = it / kTW, q = it - rg * kTW, x = x0 + q;
+      float mo[5][4];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float col[WIN];
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) col[k] = sh[(j * IH + 4 * rg + k) * kTW + q];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < FS; ++k) s = fmaf(p.filt[k], col[o + k], s);
+          mo[j][o] = s;
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int y = y0 + 4 * rg + o;
+        if (y < H && x < W) {
+          const float mu00 = mo[0][o] * mo[0][o], mu11 = mo[1][o] * mo[1][o], mu01 = mo[0][o] * mo[1][o];
+          const float s00 = fmaxf(mo[2][o] - mu00, 0.f), s11 = fmaxf(mo[3][o] - mu11, 0.f);
+          float s01 = mo[4][o] - mu01;
+          const float lim = fminf(sqrtf(s00 * s11), fabsf(s01));
+          s01 = s01 > 0.f ? lim : (s01 < 0.f ? -lim : 0.f);
+          const float numer = (2.f * mu01 + p.c1) * (2.f * s01 + p.c2);
+          const float denom = (mu00 + mu11 + p.c1) * (s00 + s11 + p.c2);
+          const float val = numer / denom;
+          acc_ssim += (double)val;
+          if (ssim_map) ssim_map[((size_t)c * H + y) * W + x] = val;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __shared__ double red[2][kThreads / 32];
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_ssim += __shfl_down_sync(0xffffffffu, acc_ssim, o);
+    acc_se += __shfl_down_sync(0xffffffffu, acc_se, o);
+  }
+  if ((tid & 31) == 0) {
+    red[0][tid >> 5] = acc_ssim;
+    red[1][tid >> 5] = acc_se;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0, e = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      s += red[0][w];
+      e += red[1][w];
+    }
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    partials[2 * bid] = s;
+    partials[2 * bid + 1] = e;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) metrics_finalize_kernel(int nblocks, double count,
                                                                    const double* __restrict__ partials,
                                                                    float* __restrict__ out) {
@@ -177,8 +306,17 @@ extern "C" int nerfb_image_metrics(int H, int W, int C, const float* img1, const
   if (smem > 48 * 1024)   // only for windows wider than 27 taps
     NERFB_CUDA(cudaFuncSetAttribute(ssim_mse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(W, kTW), cdiv(H, kTH));
-  ssim_mse_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(H, W, C, img1, img2, p, ssim_map,
-                                                               reinterpret_cast<double*>(workspace));
+  static const bool force_generic = getenv("NERFB_SSIM_GENERIC") != nullptr;      // A/B measurements only
+  if (filter_size == 11 && !force_generic) {     // the reference's default window: register-window kernel, 32x32 tiles
+    constexpr int FS = 11, TH = 32, IHf = TH + 2 * (FS / 2), IWPf = (kTW + 2 * (FS / 2) + 3) / 4 * 4;
+    const size_t smem_f = (size_t)(2 * IHf * IWPf + 5 * IHf * kTW) * sizeof(float);
+    grid = dim3(cdiv(W, kTW), cdiv(H, TH));
+    ssim_mse_fixed_kernel<FS><<<grid, kThreads, smem_f, as_stream(stream)>>>(H, W, C, img1, img2, p, ssim_map,
+                                                                            reinterpret_cast<double*>(workspace));
+  } else {
+    ssim_mse_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(H, W, C, img1, img2, p, ssim_map,
+                                                                 reinterpret_cast<double*>(workspace));
+  }
   int rc = check_launch("ssim_mse_kernel");
   if (rc) return rc;
   metrics_finalize_kernel<<<1, kThreads, 0, as_stream(stream)>>>((int)(grid.x * grid.y), (double)H * W * C,
