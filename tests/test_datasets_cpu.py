@@ -65,3 +65,32 @@ def test_llff_minify_when_directory_missing(tmp_path):
     assert tuple(poses[0, :, 4]) == (16.0, 24.0, 815.0 / 2)
     with _quiet():
         assert D._load_data(root, factor=None, load_imgs=False)[0].shape == (3, 5, 3)
+
+
+def test_train_driver_dataset_dispatch(tmp_path):
+    """trainer.load_dataset = the dataset block of train() (ipynb:1017-1098): Blender white-background compositing and
+    near/far = 2/6; LLFF holdout selection, NDC bounds 0/1 or bounds from `bds` with no_ndc; unknown types rejected."""
+    import types
+    from nerf_projects_b200 import trainer
+    from nerf_projects_b200 import datasets as D
+    b = DS.write_blender(str(tmp_path / "blender"))
+    raw = D.load_blender_data(b, False, 2)[0]
+    args = types.SimpleNamespace(dataset_type="blender", datadir=b, half_res=False, testskip=2, white_bkgd=True)
+    images, poses, render_poses, hwf, (i_train, i_val, i_test), near, far = trainer.load_dataset(args)
+    assert (near, far) == (2., 6.) and images.shape == (5 + 2 + 3, 12, 16, 3) and len(i_train) == 5 and len(i_test) == 3
+    assert np.array_equal(images, raw[..., :3] * raw[..., -1:] + (1. - raw[..., -1:]))
+    args.white_bkgd = False
+    assert np.array_equal(trainer.load_dataset(args)[0], raw[..., :3])
+    ll = DS.write_llff(str(tmp_path / "llff"))
+    args = types.SimpleNamespace(dataset_type="llff", datadir=ll, factor=4, spherify=False, llffhold=3, no_ndc=False)
+    with _quiet():
+        images, poses, render_poses, hwf, (i_train, i_val, i_test), near, far = trainer.load_dataset(args)
+    assert (near, far) == (0., 1.) and list(i_test) == [0, 3, 6] and list(i_train) == [1, 2, 4, 5]
+    assert poses.shape == (7, 3, 4) and tuple(hwf) == (24.0, 32.0, 815.0 / 4) and render_poses.shape == (120, 3, 5)
+    args.no_ndc, args.llffhold = True, 0
+    with _quiet():
+        out = trainer.load_dataset(args)
+        bds = D.load_llff_data(ll, 4)[2]
+    assert abs(out[5] - float(bds.min()) * .9) < 1e-6 and abs(out[6] - float(bds.max())) < 1e-6 and len(out[4][2]) == 1
+    with pytest.raises(ValueError):
+        trainer.load_dataset(types.SimpleNamespace(dataset_type="deepvoxels", datadir="."))
