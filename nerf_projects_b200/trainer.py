@@ -78,9 +78,15 @@ def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
     if _get(args, "render_test", False):
         render_poses = np.array(poses[i_test])
     os.makedirs(os.path.join(args.basedir, args.expname), exist_ok=True)
+    items = dict(args) if isinstance(args, dict) else vars(args)       # the reference's AttrDict, or any attribute object
     with open(os.path.join(args.basedir, args.expname, "args.txt"), "w") as f:
-        for k in sorted(vars(args)):
-            f.write(f"{k} = {getattr(args, k)}\n")
+        for k in sorted(items):
+            f.write(f"{k} = {items[k]}\n")
+    try:
+        from .config import save_config
+        save_config(items, os.path.join(args.basedir, args.expname, "config.yaml"))
+    except Exception as e:        # non-YAML-able values in a hand-built namespace: the text dump above is enough
+        log(f"config.yaml not written: {e}")
 
     render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer = create_nerf(args, device=device)
     dev = next(render_kwargs_train["network_fn"].parameters()).device

@@ -1,0 +1,45 @@
+"""nerf_projects_b200.config: the reference's flat YAML experiment files (nerf/yaml/*) -> attribute-access args."""
+import pytest
+
+YAML = """## === Training options ===
+N_importance: 128 ## CONFIG
+N_rand: 1024 ## CONFIG
+basedir: ./logs
+datadir: ./data/nerf_synthetic/lego
+dataset_type: blender
+expname: lego_blender200k
+ft_path: null
+half_res: true ## CONFIG
+lrate: 0.0005
+lrate_decay: 500 ## CONFIG
+no_batching: True ## PAPER CONFIGS
+raw_noise_std: 1e0
+use_viewdirs: true ## CONFIG
+white_bkgd: true ## CONFIG
+"""
+
+
+def test_load_config_reference_yaml_format(tmp_path):
+    import nerf_projects_b200 as nb
+    p = tmp_path / "lego_blender200k"
+    p.write_text(YAML)
+    args = nb.load_config(str(p))
+    assert args.N_importance == 128 and args["N_rand"] == 1024 and args.ft_path is None and args.half_res is True
+    assert args.raw_noise_std == "1e0"                     # PyYAML keeps it a string; render_rays accepts that (ipynb:312)
+    assert args.netdepth == 8 and args.netchunk == 65536 and args.N_samples == 64 and args.i_weights == 10000   # defaults
+    assert getattr(args, "rng_seed", None) is None and dict(args.items())["expname"] == "lego_blender200k"
+    args.N_rand = 4096
+    assert args["N_rand"] == 4096
+    with pytest.raises(AttributeError):
+        args.nope
+    out = tmp_path / "sub" / "config.yaml"
+    nb.save_config(args, str(out))
+    again = nb.load_config(str(out))
+    assert dict(again) == dict(args)
+    assert set(nb.default_config()) >= {"multires", "multires_views", "i_embed", "perturb", "lindisp", "no_ndc", "chunk"}
+    with pytest.raises(ValueError):
+        nb.load_config({"expname": "x", "basedir": ".", "datadir": ".", "dataset_type": "nope"})
+    with pytest.raises(ValueError):
+        nb.load_config({"expname": "x"}, defaults=False)
+    with pytest.raises(FileNotFoundError):
+        nb.load_config(str(tmp_path / "missing"))

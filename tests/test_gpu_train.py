@@ -47,7 +47,8 @@ def test_train_driver_blender_dataset_checkpoint_resume_and_metrics(tmp_path):
     H = W = 40
     data = str(tmp_path / "scene")
     _write_blender_scene(data, H, W)
-    args = types.SimpleNamespace(
+    # the reference's dict-with-attribute-access args (config.py); a plain attribute namespace works too
+    args = nb.Args(
         datadir=data, dataset_type="blender", half_res=False, testskip=1, white_bkgd=True, basedir=str(tmp_path / "logs"),
         expname="exp", multires=10, i_embed=0, use_viewdirs=True, multires_views=4, N_importance=128, N_samples=64,
         netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4, lrate_decay=500,
