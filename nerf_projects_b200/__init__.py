@@ -24,7 +24,7 @@ from .render import (batchify, batchify_rays, create_nerf, get_rays, get_rays_np
 from .data import RayBatcher, precrop_pixel_ids  # noqa: F401
 from .metrics import calculate_lpips, calculate_metrics, calculate_ssim  # noqa: F401
 from .rng import keyed_rng, step_seed  # noqa: F401
-from .datasets import load_blender_data, load_llff_data, pose_spherical  # noqa: F401
+from .datasets import load_blender_data, load_dv_data, load_LINEMOD_data, load_llff_data, pose_spherical  # noqa: F401
 from .trainer import train  # noqa: F401
 from .config import Args, default_config, load_config, save_config  # noqa: F401
 from . import ops  # noqa: F401
@@ -33,5 +33,5 @@ __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network
            "create_nerf", "NeRF", "Embedder", "get_embedder", "get_rays", "get_rays_np", "ndc_rays", "sample_pdf",
            "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids",
            "keyed_rng", "step_seed", "calculate_ssim", "calculate_metrics", "calculate_lpips",
-           "load_blender_data", "load_llff_data", "pose_spherical", "train",
+           "load_blender_data", "load_llff_data", "load_LINEMOD_data", "load_dv_data", "pose_spherical", "train",
            "Args", "default_config", "load_config", "save_config"]

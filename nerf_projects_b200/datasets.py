@@ -7,7 +7,8 @@ resident and generates ray batches there).  PNG/JPG decoding uses OpenCV (``imag
 decoded 8-bit pixels are identical).  ``_minify`` of the reference shells out to ImageMagick ``mogrify``; here a
 missing ``images_<factor>`` directory is produced with ``cv2.resize(INTER_AREA)`` instead (same geometry, not
 bit-identical pixels) -- pre-minified directories are used as they are.
-LINEMOD / DeepVoxels loaders are not provided (not named by BASELINE.json).
+``load_LINEMOD_data`` (load_LINEMOD.py:36-95) and ``load_dv_data`` (load_deepvoxels.py:6-110) complete the dataset
+types ``train()`` dispatches on.
 """
 from __future__ import annotations
 
@@ -256,3 +257,87 @@ def load_llff_data(basedir, factor=8, recenter=True, bd_factor=.75, spherify=Fal
     i_test = np.argmin(np.sum(np.square(c2w[:3, 3] - poses[:, :3, 3]), -1))
     print("HOLDOUT view is", i_test)
     return images.astype(np.float32), poses.astype(np.float32), bds, render_poses, i_test
+
+
+# ------------------------------------------------------------------ LINEMOD
+
+def load_LINEMOD_data(basedir, half_res=False, testskip=1):
+    """load_LINEMOD.py:36-95 -> (imgs, poses, render_poses, [H, W, focal], K, i_split, near, far).  Like the Blender
+    format, but ``file_path`` is used as written, intrinsics come from the first frame's ``intrinsic_matrix`` and
+    near / far from the train and test metadata (floor of the smaller near, ceil of the larger far)."""
+    metas = {}
+    for split in ("train", "val", "test"):
+        with open(os.path.join(basedir, f"transforms_{split}.json")) as fp:
+            metas[split] = json.load(fp)
+    imgs, poses, i_split, start = [], [], [], 0
+    for split in ("train", "val", "test"):
+        step = 1 if (split == "train" or testskip == 0) else testskip
+        frames = metas[split]["frames"][::step]
+        if split == "test":
+            for k, f in enumerate(frames):
+                print(f"{k}th test frame: {f['file_path']}")
+        imgs.append((np.array([_imread(f["file_path"]) for f in frames]) / 255.).astype(np.float32))
+        poses.append(np.array([f["transform_matrix"] for f in frames]).astype(np.float32))
+        i_split.append(np.arange(start, start + len(frames)))
+        start += len(frames)
+    imgs, poses = np.concatenate(imgs, 0), np.concatenate(poses, 0)
+    H, W = imgs[0].shape[:2]
+    K = metas["test"]["frames"][0]["intrinsic_matrix"]          # the last split read, as the reference
+    focal = float(K[0][0])
+    print(f"Focal: {focal}")
+    render_poses = torch.stack([pose_spherical(a, -30.0, 4.0) for a in np.linspace(-180, 180, 40 + 1)[:-1]], 0)
+    if half_res:
+        import cv2
+        H, W, focal = H // 2, W // 2, focal / 2.
+        half = np.zeros((imgs.shape[0], H, W, imgs.shape[-1]))
+        for i, im in enumerate(imgs):
+            half[i] = cv2.resize(im, (W, H), interpolation=cv2.INTER_AREA)
+        imgs = half
+    near = np.floor(min(metas["train"]["near"], metas["test"]["near"]))
+    far = np.ceil(max(metas["train"]["far"], metas["test"]["far"]))
+    return imgs, poses, render_poses, [H, W, focal], K, i_split, near, far
+
+
+# --------------------------------------------------------------- DeepVoxels
+
+def _dv_focal(path, side):
+    """Focal length of intrinsics.txt rescaled to a `side`-pixel image (load_deepvoxels.py:9-48): line 1 = f cx cy,
+    line 5 = height width."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    focal = float(lines[0].split()[0])
+    height = float(lines[4].split()[0])
+    return side / height * focal
+
+
+def _dv_poses(posedir):
+    """All pose/*.txt (4x4, row-major) with the y and z camera axes flipped -> [N,3,4] fp32 (load_deepvoxels.py:64-75)."""
+    files = [f for f in sorted(os.listdir(posedir)) if f.endswith("txt")]
+    mats = np.stack([np.array([float(x) for x in open(os.path.join(posedir, f)).read().split()])
+                     .reshape(4, 4).astype(np.float32) for f in files], 0)
+    flip = np.diag([1., -1., -1., 1.])
+    return (mats @ flip)[:, :3, :4].astype(np.float32)
+
+
+def _dv_images(imgdir, step=1):
+    files = [f for f in sorted(os.listdir(imgdir)) if f.endswith("png")][::step]
+    return np.stack([_imread(os.path.join(imgdir, f)) / 255. for f in files], 0).astype(np.float32)
+
+
+def load_dv_data(scene="cube", basedir="/data/deepvoxels", testskip=8):
+    """load_deepvoxels.py:6-110 -> (imgs, poses [N,3,4], render_poses = test poses, [512, 512, focal], i_split);
+    all training views, every ``testskip``-th validation / test view."""
+    H = W = 512
+    root = lambda split: "{}/{}/{}".format(basedir, split, scene)
+    focal = _dv_focal(os.path.join(root("train"), "intrinsics.txt"), H)
+    poses = _dv_poses(os.path.join(root("train"), "pose"))
+    testposes = _dv_poses(os.path.join(root("test"), "pose"))[::testskip]
+    valposes = _dv_poses(os.path.join(root("validation"), "pose"))[::testskip]
+    parts = [_dv_images(os.path.join(root("train"), "rgb")), _dv_images(os.path.join(root("validation"), "rgb"), testskip),
+             _dv_images(os.path.join(root("test"), "rgb"), testskip)]
+    counts = np.cumsum([0] + [x.shape[0] for x in parts])
+    i_split = [np.arange(counts[i], counts[i + 1]) for i in range(3)]
+    imgs = np.concatenate(parts, 0)
+    poses = np.concatenate([poses, valposes, testposes], 0)
+    print(poses.shape, imgs.shape)
+    return imgs, poses, testposes, [H, W, focal], i_split

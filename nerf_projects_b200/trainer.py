@@ -3,8 +3,7 @@ reduced to what drives the path: dataset selection and near/far bounds (ipynb:10
 the ray-batch producer (device-side ``RayBatcher``), render -> MSE(rgb)+MSE(rgb0) -> backward -> Adam ->
 exponential lr decay (ipynb:1258-1282), checkpoints in the reference's ``.tar`` layout (ipynb:1290-1299) and the
 periodic test-set render with on-GPU metrics (ipynb:1315-1385).  Same ``args`` attribute names as the reference
-(missing optional attributes take the reference yaml defaults).  Logging to CSV/JSONL, MP4 writing and the LINEMOD /
-DeepVoxels datasets are out of scope.
+(missing optional attributes take the reference yaml defaults).  Logging to CSV/JSONL and MP4 writing are out of scope.
 
 Additions, all optional: ``data=`` passes arrays instead of reading ``args.datadir``; ``N_iters=`` replaces the
 notebook's global; ``args.rng_seed`` switches perturb / noise draws to the keyed generator (rng.py); under an
@@ -32,7 +31,7 @@ def _get(args, name, default):
 
 
 def load_dataset(args):
-    """(images [N,H,W,3], poses [N,3|4,4], render_poses, hwf, (i_train, i_val, i_test), near, far) -- ipynb:1017-1098."""
+    """(images [N,H,W,3], poses [N,3|4,4], render_poses, hwf, (i_train, i_val, i_test), near, far[, K]) -- ipynb:1017-1098."""
     from . import datasets as D
     if args.dataset_type == "llff":
         images, poses, bds, render_poses, i_test = D.load_llff_data(
@@ -57,7 +56,20 @@ def load_dataset(args):
         else:
             images = images[..., :3]
         return images, poses, render_poses, hwf, tuple(i_split), 2., 6.
-    raise ValueError(f"Unknown dataset type {args.dataset_type!r} (supported: 'blender', 'llff')")
+    if args.dataset_type == "LINEMOD":
+        images, poses, render_poses, hwf, K, i_split, near, far = D.load_LINEMOD_data(
+            args.datadir, _get(args, "half_res", False), _get(args, "testskip", 8))
+        if args.white_bkgd and images.shape[-1] == 4:
+            images = images[..., :3] * images[..., -1:] + (1. - images[..., -1:])
+        else:
+            images = images[..., :3]
+        return images, poses, render_poses, hwf, tuple(i_split), float(near), float(far), np.array(K, dtype=np.float64)
+    if args.dataset_type == "deepvoxels":
+        images, poses, render_poses, hwf, i_split = D.load_dv_data(scene=_get(args, "shape", "greek"), basedir=args.datadir,
+                                                                   testskip=_get(args, "testskip", 8))
+        hemi_R = float(np.mean(np.linalg.norm(poses[:, :3, -1], axis=-1)))       # ipynb:1091-1094
+        return images, poses, render_poses, hwf, tuple(i_split), hemi_R - 1., hemi_R + 1.
+    raise ValueError(f"Unknown dataset type {args.dataset_type!r} (supported: 'blender', 'llff', 'LINEMOD', 'deepvoxels')")
 
 
 def save_checkpoint(path, global_step, render_kwargs_train, optimizer):
@@ -71,10 +83,12 @@ def save_checkpoint(path, global_step, render_kwargs_train, optimizer):
 
 def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
     """Runs the optimisation loop; returns {'global_step', 'losses', 'psnrs', 'test_metrics', 'render_kwargs_test', ...}."""
-    images, poses, render_poses, hwf, (i_train, i_val, i_test), near, far = data if data is not None else load_dataset(args)
+    loaded = data if data is not None else load_dataset(args)
+    images, poses, render_poses, hwf, (i_train, i_val, i_test), near, far = loaded[:7]
     H, W, focal = int(hwf[0]), int(hwf[1]), float(hwf[2])
     hwf = [H, W, focal]
-    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    # intrinsics: the dataset's own matrix when it has one (LINEMOD), else a centred pinhole (ipynb:1104-1112)
+    K = loaded[7] if len(loaded) > 7 and loaded[7] is not None else np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
     if _get(args, "render_test", False):
         render_poses = np.array(poses[i_test])
     os.makedirs(os.path.join(args.basedir, args.expname), exist_ok=True)

@@ -46,3 +46,40 @@ def write_llff(root, H=24, W=32, n=7, factor=4, seed=1):
         rows.append(np.concatenate([pose.reshape(-1), [1.2 + rng.uniform(0, 0.5), 9.0 + rng.uniform(0, 6)]]))
     np.save(os.path.join(root, "poses_bounds.npy"), np.array(rows))
     return root
+
+
+def write_linemod(root, H=10, W=14, n=(4, 3, 5), seed=2):
+    """LINEMOD-format tree: like Blender, but file_path is a full path, frames carry intrinsic_matrix, metas carry near/far."""
+    import cv2
+    rng = np.random.Generator(np.random.PCG64(seed))
+    os.makedirs(root, exist_ok=True)
+    for si, (split, cnt) in enumerate(zip(("train", "val", "test"), n)):
+        os.makedirs(os.path.join(root, split), exist_ok=True)
+        frames = []
+        for i in range(cnt):
+            rgb = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+            path = os.path.join(root, split, f"{i:04d}.png")
+            cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+            m = np.eye(4)
+            m[:3, :4] = rng.normal(size=(3, 4))
+            Km = [[572.4 + si, 0.0, 325.3], [0.0, 573.6, 242.0], [0.0, 0.0, 1.0]]
+            frames.append({"file_path": path, "transform_matrix": m.tolist(), "intrinsic_matrix": Km})
+        with open(os.path.join(root, f"transforms_{split}.json"), "w") as f:
+            json.dump({"near": 0.31 + 0.2 * si, "far": 1.42 + 0.3 * si, "frames": frames}, f)
+    return root
+
+
+def write_deepvoxels(root, scene="cube", side=9, n=(5, 9, 10), seed=3):
+    """DeepVoxels-format tree: {train,validation,test}/<scene>/{intrinsics.txt, pose/*.txt, rgb/*.png}."""
+    import cv2
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for split, cnt in zip(("train", "validation", "test"), n):
+        d = os.path.join(root, split, scene)
+        os.makedirs(os.path.join(d, "pose"), exist_ok=True)
+        os.makedirs(os.path.join(d, "rgb"), exist_ok=True)
+        with open(os.path.join(d, "intrinsics.txt"), "w") as f:
+            f.write("525.0 256.0 256.0 0.\n0. 0. 0.\n1.\n0.5\n480 640\n")
+        for i in range(cnt):
+            np.savetxt(os.path.join(d, "pose", f"{i:06d}.txt"), rng.normal(size=(1, 16)), fmt="%.8f")
+            cv2.imwrite(os.path.join(d, "rgb", f"{i:06d}.png"), rng.integers(0, 256, size=(side, side, 3), dtype=np.uint8))
+    return root

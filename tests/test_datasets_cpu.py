@@ -92,5 +92,35 @@ def test_train_driver_dataset_dispatch(tmp_path):
         out = trainer.load_dataset(args)
         bds = D.load_llff_data(ll, 4)[2]
     assert abs(out[5] - float(bds.min()) * .9) < 1e-6 and abs(out[6] - float(bds.max())) < 1e-6 and len(out[4][2]) == 1
+    lm = DS.write_linemod(str(tmp_path / "linemod"))
+    with _quiet():
+        out = trainer.load_dataset(types.SimpleNamespace(dataset_type="LINEMOD", datadir=lm, half_res=False, testskip=1,
+                                                         white_bkgd=True))
+    assert out[0].shape == (12, 10, 14, 3) and (out[5], out[6]) == (0.0, 3.0) and out[7].shape == (3, 3) and out[7][0, 0] == 574.4
+    dv = DS.write_deepvoxels(str(tmp_path / "dv"))
+    with _quiet():
+        out = trainer.load_dataset(types.SimpleNamespace(dataset_type="deepvoxels", datadir=dv, shape="cube", testskip=8))
+    assert len(out) == 7 and abs((out[6] - out[5]) - 2.0) < 1e-6 and out[3][0] == 512
     with pytest.raises(ValueError):
-        trainer.load_dataset(types.SimpleNamespace(dataset_type="deepvoxels", datadir="."))
+        trainer.load_dataset(types.SimpleNamespace(dataset_type="nope", datadir="."))
+
+
+def test_load_linemod_and_deepvoxels_vs_reference(tmp_path):
+    from nerf_projects_b200 import datasets as D
+    g = gold("datasets")
+    lm = DS.write_linemod(str(tmp_path / "linemod"))
+    for tag, kw in (("m_full", dict(half_res=False, testskip=1)), ("m_half", dict(half_res=True, testskip=2))):
+        with _quiet():
+            imgs, poses, rp, hwf, K, i_split, near, far = D.load_LINEMOD_data(lm, **kw)
+        assert imgs.dtype == g[tag + ".imgs"].dtype and np.array_equal(imgs, g[tag + ".imgs"]), tag
+        assert np.array_equal(poses, g[tag + ".poses"]) and np.array_equal(np.array(hwf, np.float64), g[tag + ".hwf"])
+        assert np.array_equal(np.array(K, np.float64), g[tag + ".K"]) and np.array_equal(i_split[2], g[tag + ".i_test"])
+        assert float(near) == float(g[tag + ".near"]) and float(far) == float(g[tag + ".far"]) and rp.shape == (40, 4, 4)
+    dv = DS.write_deepvoxels(str(tmp_path / "dv"))
+    for tag, skip in (("d_skip8", 8), ("d_skip3", 3)):
+        with _quiet():
+            imgs, poses, rp, hwf, i_split = D.load_dv_data(scene="cube", basedir=dv, testskip=skip)
+        assert imgs.dtype == np.float32 and np.array_equal(imgs, g[tag + ".imgs"]), tag
+        assert poses.dtype == np.float32 and np.array_equal(poses, g[tag + ".poses"])
+        assert np.array_equal(rp, g[tag + ".render_poses"]) and np.array_equal(np.array(hwf, np.float64), g[tag + ".hwf"])
+        assert np.array_equal(i_split[1], g[tag + ".i_val"]) and np.array_equal(i_split[2], g[tag + ".i_test"])

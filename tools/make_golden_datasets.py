@@ -57,6 +57,21 @@ def main():
             images, poses, bds, rp, i_test = LL.load_llff_data(ll, **kw)
             out.update({f"{tag}.images": images, f"{tag}.poses": poses, f"{tag}.bds": bds, f"{tag}.render_poses": rp,
                         f"{tag}.i_test": np.int64(i_test)})
+    import load_LINEMOD as LM
+    import load_deepvoxels as DV
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()):
+        # LINEMOD frames carry full paths: a fixed location so that the fixture does not depend on the temp name
+        lm = DS.write_linemod(os.path.join(tmp, "linemod"))
+        for tag, kw in (("m_full", dict(half_res=False, testskip=1)), ("m_half", dict(half_res=True, testskip=2))):
+            imgs, poses, rp, hwf, K, i_split, near, far = LM.load_LINEMOD_data(lm, **kw)
+            out.update({f"{tag}.imgs": imgs, f"{tag}.poses": poses, f"{tag}.hwf": np.array(hwf, np.float64),
+                        f"{tag}.K": np.array(K, np.float64), f"{tag}.near": np.float64(near), f"{tag}.far": np.float64(far),
+                        f"{tag}.i_test": i_split[2]})
+        dv = DS.write_deepvoxels(os.path.join(tmp, "dv"))
+        for tag, skip in (("d_skip8", 8), ("d_skip3", 3)):
+            imgs, poses, rp, hwf, i_split = DV.load_dv_data(scene="cube", basedir=dv, testskip=skip)
+            out.update({f"{tag}.imgs": imgs, f"{tag}.poses": poses, f"{tag}.render_poses": rp,
+                        f"{tag}.hwf": np.array(hwf, np.float64), f"{tag}.i_val": i_split[1], f"{tag}.i_test": i_split[2]})
     out["pose_spherical"] = np.stack([LB.pose_spherical(a, p, r).numpy() for a, p, r in
                                       ((0., -30., 4.), (37.5, -30., 4.), (-180., 12., 2.5), (91., 0., 1.))])
     path = os.path.join(ROOT, "tests", "golden", "datasets.npz")
