@@ -2,7 +2,7 @@
 reduced to what drives the path: dataset selection and near/far bounds (ipynb:1017-1098), ``create_nerf``,
 the ray-batch producer (device-side ``RayBatcher``), render -> MSE(rgb)+MSE(rgb0) -> backward -> Adam ->
 exponential lr decay (ipynb:1258-1282), checkpoints in the reference's ``.tar`` layout (ipynb:1290-1299) and the
-periodic test-set render with on-GPU metrics (ipynb:1315-1385).  Same ``args`` attribute names as the reference
+periodic validation-trajectory and test-set renders with on-GPU metrics (ipynb:1301-1385).  Same ``args`` attribute names as the reference
 (missing optional attributes take the reference yaml defaults).  Logging to CSV/JSONL and MP4 writing are out of scope.
 
 Additions, all optional: ``data=`` passes arrays instead of reading ``args.datadir``; ``N_iters=`` replaces the
@@ -143,6 +143,7 @@ def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
     seed = _get(args, "rng_seed", None)
     losses, psnrs, test_metrics = [], [], {}
     i_print, i_weights, i_testset = _get(args, "i_print", 100), _get(args, "i_weights", 10000), _get(args, "i_testset", 50000)
+    i_video = _get(args, "i_video", 50000)
     t0 = time.time()
     for i in range(start + 1, N_iters):
         global_step = i
@@ -173,6 +174,14 @@ def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
             path = os.path.join(args.basedir, args.expname, "checkpoints", f"{i:06d}.tar")
             save_checkpoint(path, global_step, render_kwargs_train, optimizer)
             log("Saved checkpoints at", path)
+        if i % i_video == 0 and i > 0 and (not dist.is_initialized() or dist.get_rank() == 0):
+            # validation trajectory (ipynb:1301-1310); frames are kept as arrays (MP4 writing needs imageio-ffmpeg)
+            with torch.no_grad():
+                rgbs, disps = render_path(render_poses, hwf, K, chunk, render_kwargs_test)[:2]
+            base = os.path.join(args.basedir, args.expname, "{}_spiral_{:06d}_".format(args.expname, i))
+            np.save(base + "rgb.npy", (255 * np.clip(rgbs, 0, 1)).astype(np.uint8))
+            np.save(base + "disp.npy", (255 * np.clip(disps / max(float(np.max(disps)), 1e-10), 0, 1)).astype(np.uint8))
+            log("Done, saving", rgbs.shape, disps.shape)
         if i % i_testset == 0 and i > 0 and len(i_test) > 0:
             test_metrics[i] = testset(i, "testset")
             log(f"[TEST] Iter: {i} " + " ".join(f"{k}: {v:.4f}" for k, v in test_metrics[i].items()))

@@ -53,7 +53,7 @@ def test_train_driver_blender_dataset_checkpoint_resume_and_metrics(tmp_path):
         expname="exp", multires=10, i_embed=0, use_viewdirs=True, multires_views=4, N_importance=128, N_samples=64,
         netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4, lrate_decay=500,
         ft_path=None, no_reload=False, perturb=1.0, raw_noise_std=0.0, no_ndc=False, lindisp=False, N_rand=1024,
-        no_batching=False, precrop_iters=0, precrop_frac=0.5, chunk=32768, i_print=1, i_weights=100, i_testset=200,
+        no_batching=False, precrop_iters=0, precrop_frac=0.5, chunk=32768, i_print=1, i_weights=100, i_testset=200, i_video=200,
         rng_seed=7)
     torch.manual_seed(0)
     out = nb.train(args, N_iters=201, log=lambda *a: None)
@@ -73,6 +73,10 @@ def test_train_driver_blender_dataset_checkpoint_resume_and_metrics(tmp_path):
     m = out["test_metrics"][200]
     assert set(m) >= {"avg_psnr", "avg_ssim", "avg_mse", "std_psnr"} and m["avg_psnr"] > 5 and 0 < m["avg_ssim"] <= 1
     assert len([f for f in os.listdir(os.path.join(args.basedir, "exp", "testset_000200")) if f[:3].isdigit()]) == 2
+    # validation trajectory of the 40 spherical render poses, saved as uint8 arrays
+    spiral = np.load(os.path.join(args.basedir, "exp", "exp_spiral_000200_rgb.npy"))
+    assert spiral.shape == (40, H, W, 3) and spiral.dtype == np.uint8 and spiral.std() > 1
+    assert os.path.exists(os.path.join(args.basedir, "exp", "config.yaml")) and os.path.exists(os.path.join(args.basedir, "exp", "args.txt"))
     # resume: create_nerf picks up 000200.tar, the loop continues at 201 (here: per-image sampling with centre crop)
     args.no_batching, args.precrop_iters = True, 205
     out2 = nb.train(args, N_iters=211, log=lambda *a: None)
