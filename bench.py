@@ -138,6 +138,27 @@ def cpu_reference_rate(n_rays: int, steps: int, warmup: int):
     return n_rays / dt, dt, cores
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, whatever the libraries print (NCCL's version banner goes to fd 1 from C):
+    keep a private duplicate of fd 1 for the result and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,7 +172,7 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                              "sample": f"{n}-ray subset of the 800x800 frame, 64+128, viewdirs; torch CPU fp32, {cores} threads"},
             "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -165,6 +186,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step leg")
     ap.add_argument("--no-llff", action="store_true", help="skip the extra LLFF-shaped (NDC) render leg")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -181,8 +203,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own output (version banner, NCCL_DEBUG=INFO lines) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     warmup = max(3, args.warmup)
@@ -363,7 +383,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"{n}-ray subset of the same frame (64+128, viewdirs), oracle port on "
                                               f"torch CPU fp32 with {cores} threads, {dt:.1f} s"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
