@@ -102,3 +102,21 @@ def test_header_is_plain_c(tmp_path):
                 ["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++"]):
         res = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def test_library_sass_uses_the_blackwell_tensor_and_copy_engines():
+    """Static evidence that the shipped library is the sm_100a path (no mma.sync / wmma recompile): tcgen05.mma (UTCHMMA),
+    tcgen05.ld (LDTM), tcgen05.commit (UTCBAR), tensor-map TMA loads (UTMALDG) and bulk async copies (UBLKCP) in its SASS."""
+    import shutil
+    import subprocess
+    from nerf_projects_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(_lib.LIB_PATH):
+        from nerf_projects_b200 import build
+        build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for op, at_least in (("UTCHMMA", 50), ("LDTM", 10), ("UTCBAR", 5), ("UTMALDG", 2), ("UBLKCP", 5)):
+        assert sass.count(op) >= at_least, f"{op}: {sass.count(op)} occurrences"
+    assert "HMMA.16816" not in sass and "WGMMA" not in sass          # no legacy warp-level tensor-core path
