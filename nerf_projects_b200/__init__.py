@@ -26,7 +26,8 @@ from .metrics import calculate_lpips, calculate_metrics, calculate_ssim  # noqa:
 from .rng import keyed_rng, step_seed  # noqa: F401
 from .datasets import load_blender_data, load_dv_data, load_LINEMOD_data, load_llff_data, pose_spherical  # noqa: F401
 from .trainer import train  # noqa: F401
-from .config import Args, default_config, load_config, save_config  # noqa: F401
+from .config import (Args, AttrDict, create_default_config, default_config, load_config, load_or_create_config,  # noqa: F401
+                     load_yaml, save_config, save_yaml, validate_config)
 from . import ops  # noqa: F401
 
 __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network", "batchify", "raw2outputs",
@@ -34,4 +35,5 @@ __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network
            "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids",
            "keyed_rng", "step_seed", "calculate_ssim", "calculate_metrics", "calculate_lpips",
            "load_blender_data", "load_llff_data", "load_LINEMOD_data", "load_dv_data", "pose_spherical", "train",
-           "Args", "default_config", "load_config", "save_config"]
+           "Args", "default_config", "load_config", "save_config", "AttrDict", "load_yaml", "save_yaml",
+           "create_default_config", "validate_config", "load_or_create_config"]

@@ -55,8 +55,8 @@ def default_config() -> Dict[str, Any]:
 _REQUIRED = ("expname", "basedir", "datadir", "dataset_type")
 
 
-def validate_config(cfg: Dict[str, Any]) -> bool:
-    """Required keys present, counts positive, dataset type known (utils.py:134-181)."""
+def _check_config(cfg: Dict[str, Any]) -> bool:
+    """load_config's own check (raises): identification keys present, counts positive, dataset type known."""
     for k in _REQUIRED:
         if k not in cfg:
             raise ValueError(f"Missing required configuration key: {k}")
@@ -82,7 +82,7 @@ def load_config(source, defaults: bool = True) -> Args:
             raise ValueError(f"Configuration file is empty: {source}")
     cfg = default_config() if defaults else {}
     cfg.update(loaded)
-    validate_config(cfg)
+    _check_config(cfg)
     return Args.wrap(cfg)
 
 
@@ -91,3 +91,75 @@ def save_config(cfg: Dict[str, Any], path: str) -> None:
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with open(path, "w", encoding="utf-8") as f:
         yaml.dump(dict(cfg), f, default_flow_style=False, indent=2)
+
+
+# ---- the reference's own names (nerf/utils.py, notebook AttrDict cell), same behaviour: plain dicts in and out,
+# ---- validate_config reports by return value and message instead of raising
+
+class AttrDict(Args):
+    __slots__ = ()
+
+    @classmethod
+    def from_obj(cls, obj):
+        return cls.wrap(obj)
+
+
+_REFERENCE_REQUIRED = ("expname", "basedir", "datadir", "netdepth", "netwidth", "netdepth_fine", "netwidth_fine", "N_rand",
+                       "lrate", "lrate_decay", "chunk", "netchunk", "N_samples", "N_importance", "perturb", "use_viewdirs",
+                       "i_embed", "multires", "multires_views", "raw_noise_std", "dataset_type")
+
+
+def validate_config(config: Dict[str, Any]) -> bool:
+    """utils.py:134-181: True when every required key is present and netdepth / netwidth / lrate / N_samples / chunk > 0."""
+    missing = [k for k in _REFERENCE_REQUIRED if k not in config]
+    if missing:
+        print(f"Missing required configuration keys: {missing}")
+        return False
+    for key, what in (("netdepth", "Network depth (netdepth)"), ("netwidth", "Network width (netwidth)"),
+                      ("lrate", "Learning rate (lrate)"), ("N_samples", "Number of samples (N_samples)"),
+                      ("chunk", "Chunk size (chunk)")):
+        if config[key] <= 0:
+            print(f"{what} must be positive")
+            return False
+    return True
+
+
+def load_yaml(config_path: str) -> Dict[str, Any]:
+    """utils.py:8-39: the file's own keys as a plain dict (no defaults filled in)."""
+    return _plain_yaml(config_path)
+
+
+def _plain_yaml(path):
+    import yaml
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Configuration file not found: {path}")
+    with open(path, "r", encoding="utf-8") as f:
+        cfg = yaml.safe_load(f)
+    if cfg is None:
+        raise ValueError(f"Configuration file is empty: {path}")
+    return cfg
+
+
+def save_yaml(config: Dict[str, Any], config_path: str) -> None:
+    save_config(config, config_path)
+
+
+def create_default_config() -> Dict[str, Any]:
+    return default_config()
+
+
+def load_or_create_config(config_path: str) -> Dict[str, Any]:
+    """utils.py:183-208: load the file, or write the defaults there first; validation is reported, not enforced."""
+    if os.path.exists(config_path):
+        print(f"Loading configuration from {config_path}")
+        config = load_yaml(config_path)
+    else:
+        print(f"Configuration file {config_path} not found, creating default config")
+        config = create_default_config()
+        save_yaml(config, config_path)
+        print(f"Default configuration saved to {config_path}")
+    if not validate_config(config):
+        print("Warning: Configuration validation failed")
+    else:
+        print("Configuration validation passed! Arguments are valid and correctly set.")
+    return config

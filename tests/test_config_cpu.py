@@ -43,3 +43,24 @@ def test_load_config_reference_yaml_format(tmp_path):
         nb.load_config({"expname": "x"}, defaults=False)
     with pytest.raises(FileNotFoundError):
         nb.load_config(str(tmp_path / "missing"))
+
+
+def test_reference_named_config_helpers(tmp_path, capsys):
+    """nerf/utils.py names with the reference's behaviour: plain dicts, validate_config returns a bool."""
+    import nerf_projects_b200 as nb
+    p = tmp_path / "cfg.yaml"
+    cfg = nb.load_or_create_config(str(p))                  # missing -> defaults written, validated, returned
+    assert p.exists() and cfg == nb.create_default_config() and nb.validate_config(cfg) is True
+    assert nb.load_yaml(str(p)) == cfg and type(nb.load_yaml(str(p))) is dict
+    bad = dict(cfg); bad["netwidth"] = 0
+    assert nb.validate_config(bad) is False and nb.validate_config({"expname": "x"}) is False
+    assert "must be positive" in capsys.readouterr().out
+    (tmp_path / "lego").write_text(YAML)
+    partial = nb.load_yaml(str(tmp_path / "lego"))           # the file's own keys only
+    assert "netdepth" not in partial and partial["N_importance"] == 128 and nb.validate_config(partial) is False
+    a = nb.AttrDict.from_obj({"a": {"b": 1}, "c": [{"d": 2}]})
+    assert a.a.b == 1 and a.c[0].d == 2
+    a.new_key = 3
+    assert a["new_key"] == 3
+    nb.save_yaml({"k": 1}, str(tmp_path / "deep" / "x.yaml"))
+    assert nb.load_yaml(str(tmp_path / "deep" / "x.yaml")) == {"k": 1}
