@@ -37,6 +37,8 @@ class NeRF(nn.Module):
             self.output_linear = nn.Linear(W, output_ch)
         self._packed = None
         self._packed_key = None
+        self._packed_bwd = None
+        self._packed_bwd_key = None
 
     # nerf.py:57-111
     def forward(self, x):
@@ -66,14 +68,36 @@ class NeRF(nn.Module):
         dev = self.pts_linears[0].weight.device
 
         def put(lin, k):
-            lin.weight.data = torch.from_numpy(np.transpose(weights[k])).to(dev)
-            lin.bias.data = torch.from_numpy(np.transpose(weights[k + 1])).to(dev)
+            # same values as the reference's transposed views, stored contiguously (the kernels read row-major weights)
+            lin.weight.data = torch.from_numpy(np.ascontiguousarray(np.transpose(weights[k]), dtype=np.float32)).to(dev)
+            lin.bias.data = torch.from_numpy(np.ascontiguousarray(np.transpose(weights[k + 1]), dtype=np.float32)).to(dev)
         for i in range(self.D):
             put(self.pts_linears[i], 2 * i)
         put(self.feature_linear, 2 * self.D)
         put(self.views_linears[0], 2 * self.D + 2)
         put(self.rgb_linear, 2 * self.D + 4)
         put(self.alpha_linear, 2 * self.D + 6)
+        self.invalidate_packed()
+
+    def invalidate_packed(self):
+        """Drop the cached bf16 weight images of the fused kernels.  They are keyed on (data_ptr, _version) of every
+        parameter, which in-place writes through ``p.data`` (``p.data.copy_()``, EMA updates, legacy init idioms) do NOT
+        change: call this after such a write.  ``load_state_dict``, ``.to()``/``.cuda()``, optimizer steps and
+        ``load_weights_from_keras`` are covered automatically."""
+        self._packed = None
+        self._packed_key = None
+        self._packed_bwd = None
+        self._packed_bwd_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_packed()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return out
 
     # ---- helpers for the fused kernels -------------------------------
     def is_canonical(self) -> bool:
