@@ -82,3 +82,4 @@ def maps_close(got, ref, tol, min_frac=1.0, cap=None, what=""):
     if cap is not None:
         assert err.max() <= cap, f"{what}: max err {err.max():.3e} > cap {cap}"
     return int(bad.sum())
+

@@ -117,6 +117,36 @@ def test_train_grads_match_reference():
                                            rtol=1e-3, atol=1e-7 + 1e-4 * n)
 
 
+def test_c2_batch_forward_slice_matches_reference():
+    """BASELINE configs[2] fixture (4096-ray batch, tools/make_golden_c2.py): the oracle reproduces the reference's maps
+    on a 512-ray slice of the batch (the full batch + gradients are checked on the GPU box)."""
+    g = gold("train_grads_c2")
+    pc, pf = case_params("render_c1_sharp")
+    sl = slice(1024, 1536)
+    rays, _ = O.pack_rays(T(g["rays_o"][sl]), T(g["rays_d"][sl]), 2.0, 6.0, use_viewdirs=True)
+    with torch.no_grad():
+        out = O.render_rays(rays, O.to_torch(pc), O.to_torch(pf), N_samples=64, N_importance=128, white_bkgd=True, retraw=True)
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0"):
+        close(out[k], g[k][sl], 2e-6)
+    close(out["raw"][:, -1, 3], g["sigma_last"][sl], 2e-5)
+
+
+def test_discontinuity_gate_logic():
+    """oracle/discontinuity.py: the gate accepts errors beyond tol only inside the explained set and only for a few rays."""
+    from oracle import discontinuity as DS
+    err = torch.tensor([1e-5] * 198 + [0.5, 0.5])
+    explained = torch.zeros(200, dtype=torch.bool); explained[-2:] = True
+    DS.gate(err, 1e-4, explained, "ok")
+    with pytest.raises(AssertionError):
+        DS.gate(err, 1e-4, torch.zeros(200, dtype=torch.bool), "unexplained outliers")
+    many = torch.tensor([1e-5] * 180 + [0.5] * 20)
+    with pytest.raises(AssertionError):
+        DS.gate(many, 1e-4, torch.ones(200, dtype=torch.bool), "too many outliers even if explained")
+    # fp32 mode never excludes rays for sigma_last
+    raw = torch.zeros(4, 8, 4)
+    assert not DS.sigma_last_set(raw, "fp32").any() and DS.sigma_last_set(raw, "bf16").all()
+
+
 def test_metrics_oracle_vs_reference_golden():
     """oracle/metrics_np.py against the unmodified reference's calculate_ssim / calculate_metrics
     (tests/golden/metrics.npz, tools/make_golden_metrics.py).  The per-pixel map is ill-conditioned where the local
