@@ -10,7 +10,13 @@ render of an 800x800 Blender-shaped image, use_viewdirs, multires 10/4,
 random-init weights (numpy PCG64 seeds 0/1), white background, near 2 / far 6.
 One "step" = one full frame (640 000 rays) per GPU; with N GPUs a step renders
 N frames, each ray-sharded over all N ranks with one all-gather of the
-rendered tiles (weak scaling: per-GPU work is one frame's worth of rays).
+rendered tiles (weak scaling: per-GPU work is one frame's worth of rays; the
+gather of frame k runs under the render of frame k+1).  Extra legs on the same
+JSON line: `latency` (ONE frame sharded over the N GPUs, synchronised on both
+sides), `train` (4096 rays per GPU, weak) and `train_c4` (BASELINE configs[4] as
+stated: 32 768 rays per step over the N GPUs, strong), `llff` (configs[3]), `c0`
+(configs[0]: 100x100, 64 samples, no view directions -- this repo's kernel and the
+reference algorithm on the host CPU), and at N > 1 `sharded_equals_single`.
 
 Timing: CUDA events on the launching stream, barrier + synchronize on both
 sides, max over ranks.  Between timed steps the working set (2.6 GB of raw /
@@ -111,27 +117,39 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_rate(n_rays: int, steps: int, warmup: int):
-    """The reference algorithm on the host CPU (oracle port, torch CPU fp32 ops, all cores) on a
-    bounded sample of the same workload.  Returns (rays/s, seconds per step, cores)."""
+def cpu_reference_rate(n_rays: int, steps: int, warmup: int, config: str = "C1"):
+    """The reference algorithm on the host CPU (oracle port, torch CPU fp32 ops, all cores) on a bounded sample of the
+    workload: C1 = n_rays-ray subset of the 800x800 frame (64+128, viewdirs); C0 = BASELINE configs[0] in full
+    (100x100 rays, 64 samples, N_importance=0, no view directions).  Returns (rays/s, seconds per step, cores)."""
     import numpy as np
     import torch
     from oracle import nerf_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    pc = O.to_torch(O.make_params(0, use_viewdirs=True, output_ch=5))
-    pf = O.to_torch(O.make_params(1, use_viewdirs=True, output_ch=5))
-    K, c2w = O.blender_camera(H, W, 30.0)
-    ro, rd = O.get_rays(H, W, K, torch.from_numpy(c2w))
-    rng = np.random.Generator(np.random.PCG64(0))
-    idx = torch.from_numpy(np.sort(rng.choice(H * W, size=n_rays, replace=False)))
-    ro, rd = ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx]
+    if config == "C0":
+        Hc = Wc = 100
+        pc = O.to_torch(O.make_params(100, use_viewdirs=False, input_ch_views=0, output_ch=4))
+        K, c2w = O.blender_camera(Hc, Wc, 30.0)
+        ro, rd = O.get_rays(Hc, Wc, K, torch.from_numpy(c2w))
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        n_rays = Hc * Wc
+        call = lambda: O.render(Hc, Wc, K, pc, None, rays=(ro, rd), ndc=False, near=NEAR, far=FAR, use_viewdirs=False,
+                                N_samples=N_SAMPLES, N_importance=0, white_bkgd=False, chunk=32768)
+    else:
+        pc = O.to_torch(O.make_params(0, use_viewdirs=True, output_ch=5))
+        pf = O.to_torch(O.make_params(1, use_viewdirs=True, output_ch=5))
+        K, c2w = O.blender_camera(H, W, 30.0)
+        ro, rd = O.get_rays(H, W, K, torch.from_numpy(c2w))
+        rng = np.random.Generator(np.random.PCG64(0))
+        idx = torch.from_numpy(np.sort(rng.choice(H * W, size=n_rays, replace=False)))
+        ro, rd = ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx]
+        call = lambda: O.render(H, W, K, pc, pf, rays=(ro, rd), ndc=False, near=NEAR, far=FAR, use_viewdirs=True,
+                                N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, white_bkgd=True, chunk=32768)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.render(H, W, K, pc, pf, rays=(ro, rd), ndc=False, near=NEAR, far=FAR, use_viewdirs=True,
-                     N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, white_bkgd=True, chunk=32768)
+            call()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
@@ -159,20 +177,36 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+REF_SAMPLE_RAYS = 16384          # the CPU arm times a 16 384-ray subset of the frame per step
+VS_BASELINE_REASON = ("BASELINE.md holds no published number for this metric/config: the reference's only figure "
+                      "(~20.7 k rays/s) is for 96+288 evaluations per ray on an unnamed GPU")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 8192
-    rate, dt, cores = cpu_reference_rate(n, args.steps, min(args.warmup, 1))
+    n = REF_SAMPLE_RAYS
+    warmup = max(3, args.warmup)          # the same warm-up count as the GPU arm
+    rate, dt, cores = cpu_reference_rate(n, args.steps, warmup)
     line = {"impl": "reference", "metric": "rays/s (64+128 samples) render", "value": rate, "unit": "rays/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{n} of 640000 rays per step"},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "vs_baseline_reason": VS_BASELINE_REASON,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{n} of 640000 rays per step (rates are per ray)"},
             "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                              "sample": f"{n}-ray subset of the 800x800 frame, 64+128, viewdirs; torch CPU fp32, {cores} threads"},
             "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def train_traffic():
+    """Measured DRAM bytes per sample of the training kernels (forward-with-save + data-gradient chain + weight gradients)
+    from the committed ncu captures (profiles/traffic.json, key "train"); None if absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("train")
 
 
 def main():
@@ -183,8 +217,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--chunk", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step leg")
-    ap.add_argument("--no-llff", action="store_true", help="skip the extra LLFF-shaped (NDC) render leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step legs")
+    ap.add_argument("--no-llff", action="store_true", help="skip the LLFF-shaped (NDC) render leg")
+    ap.add_argument("--no-c0", action="store_true", help="skip the BASELINE configs[0] leg")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
@@ -224,15 +259,19 @@ def main():
     resident = [frame_rays(i) for i in range(world)]            # inputs resident in HBM for `value`
 
     def step_resident():
-        outs = []
-        for f in range(world):                                    # N frames per step, each sharded over N ranks
+        if world == 1:
+            ro, rd = resident[0]
+            return [nb.render(H, W, K, chunk=args.chunk, rays=(ro, rd), near=NEAR, far=FAR, **kw_test)[0]]
+        # N frames per step, each sharded over the N ranks; the tile all-gather of frame f runs on NCCL's stream under the
+        # render of frame f+1 (two buffer slots), and every gather has completed when the step ends
+        pending, outs = [], []
+        for f in range(world):
             ro, rd = resident[f]
-            if world == 1:
-                rgb, disp, acc, _ = nb.render(H, W, K, chunk=args.chunk, rays=(ro, rd), near=NEAR, far=FAR, **kw_test)
-                outs.append(rgb)
-            else:
-                outs.append(parallel.render_sharded(nb.render, H, W, K, ro, rd, chunk=args.chunk, near=NEAR, far=FAR,
-                                                    **kw_test)[0])
+            pending.append(parallel.render_sharded(nb.render, H, W, K, ro, rd, chunk=args.chunk, near=NEAR, far=FAR,
+                                                   async_gather=True, slot=f % 2, **kw_test))
+            if len(pending) == 2:
+                outs.append(pending.pop(0).wait())
+        outs += [h.wait() for h in pending]
         return outs
 
     def sync_all():
@@ -285,11 +324,37 @@ def main():
                     host_maps[f][2].copy_(acc, non_blocking=True)
                 else:       # each rank uploads its own slice of the frame's rays; rank 0 downloads the gathered tiles
                     tiles = parallel.render_sharded(nb.render, H, W, K, host_rays[f][0], host_rays[f][1], upload_to=dev,
-                                                    return_packed=True, chunk=args.chunk, near=NEAR, far=FAR, **kw_test)
+                                                    return_packed=True, slot=f % 2, chunk=args.chunk, near=NEAR, far=FAR,
+                                                    **kw_test)
                     if rank == 0:
                         host_out[f].copy_(tiles, non_blocking=True)        # one contiguous 12.8 MB copy per frame
         step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
+
+        # ---- latency of ONE frame ray-sharded over the N GPUs (synchronised on both sides; strong scaling of a frame)
+        def one_frame():
+            ro, rd = resident[0]
+            if world == 1:
+                nb.render(H, W, K, chunk=args.chunk, rays=(ro, rd), near=NEAR, far=FAR, **kw_test)
+            else:
+                parallel.render_sharded(nb.render, H, W, K, ro, rd, chunk=args.chunk, near=NEAR, far=FAR, return_packed=True,
+                                        **kw_test)
+        lat = sorted(timed(one_frame, 1) for _ in range(5))
+        latency = {"ms_per_frame": lat[len(lat) // 2], "ms_min": lat[0], "unit": "ms", "rays_per_s": n_rays / (lat[len(lat) // 2] * 1e-3),
+                   "config": f"one C1 frame (640000 rays) sharded over {world} GPU(s), barrier + synchronize on both sides, "
+                             "median of 5, rays resident in HBM, tile all-gather included"}
+
+        # ---- at N > 1: the gathered frame must be bit-equal to a single-GPU render of the same frame
+        sharded_equals_single = None
+        if world > 1:
+            ro, rd = resident[0]
+            tiles = parallel.render_sharded(nb.render, H, W, K, ro, rd, chunk=args.chunk, near=NEAR, far=FAR,
+                                            return_packed=True, **kw_test).clone()
+            rgb1, disp1, acc1, _ = nb.render(H, W, K, chunk=args.chunk, rays=(ro, rd), near=NEAR, far=FAR, **kw_test)
+            eq = torch.equal(tiles[:, 0:3], rgb1) and torch.equal(tiles[:, 3], disp1) and torch.equal(tiles[:, 4], acc1)
+            flag = torch.tensor([1 if eq else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            sharded_equals_single = bool(flag.item())
 
     # ---- extra leg: LLFF-shaped forward-facing frames (BASELINE configs[3]: 1008x756, NDC, near 0 / far 1, no white
     # background), N frames per step each ray-sharded over the N ranks, rays resident in HBM
@@ -302,11 +367,17 @@ def main():
         kw_l = dict(kw_test); kw_l.update(ndc=True, white_bkgd=False, lindisp=False)
 
         def step_llff():
-            for _ in range(world):
+            pending = []
+            for f in range(world):
                 if world == 1:
                     nb.render(Hl, Wl, Kl, chunk=args.chunk, rays=(ro_l, rd_l), near=0., far=1., **kw_l)
                 else:
-                    parallel.render_sharded(nb.render, Hl, Wl, Kl, ro_l, rd_l, chunk=args.chunk, near=0., far=1., **kw_l)
+                    pending.append(parallel.render_sharded(nb.render, Hl, Wl, Kl, ro_l, rd_l, chunk=args.chunk, near=0., far=1.,
+                                                           async_gather=True, slot=f % 2, **kw_l))
+                    if len(pending) == 2:
+                        pending.pop(0).wait()
+            for h in pending:
+                h.wait()
         with torch.no_grad():
             step_llff()
             ll_steps = 3
@@ -315,32 +386,107 @@ def main():
                 "config": f"C3: {Wl}x{Hl} LLFF-shaped NDC frame(s), coarse 64 + fine 128, use_viewdirs, "
                           f"{'ray-sharded x' + str(world) if world > 1 else 'single GPU'}"}
 
-    # ---- extra leg: one optimisation step of train() on a 4096-ray batch per GPU (BASELINE configs[2]/[4]):
-    # fused forward + backward through the kernels + fused Adam, data-parallel all-reduce when world > 1
-    train = None
+    # ---- training legs: one optimisation step of train() -- fused forward + backward through the kernels + fused Adam,
+    # data-parallel gradient all-reduce when world > 1.  `train`: 4096 rays per GPU (BASELINE configs[2]; weak);
+    # `train_c4`: BASELINE configs[4] as stated -- 32 768 rays per step sharded over the N GPUs (strong).
+    train = train_c4 = None
+    train_sharded = None
+    TRAIN_FLOP_PER_RAY = 893_190_144             # fwd + wgrad + dgrad MACs x 2 x 256 evaluations
     if not args.no_train:
         kw_tr = dict(kw_train); kw_tr.update(ndc=False, lindisp=False, perturb=1.0, raw_noise_std=1.0)
-        n_batch = 4096 * world
-        gen = torch.Generator(device=dev).manual_seed(0)
-        sel = torch.randint(0, n_rays, (n_batch,), device=dev, generator=gen)
-        b_o, b_d = resident[0][0][sel].contiguous(), resident[0][1][sel].contiguous()
-        target = torch.rand((n_batch, 3), device=dev, generator=gen)
         bucket = parallel.GradBucket(grad_vars)
-
+        gen = torch.Generator(device=dev).manual_seed(0)
         tr_count = [0]
 
-        def step_train():
-            # perturb / noise draws keyed by (seed, step, global ray index): the step does not depend on the number of GPUs
-            tr_count[0] += 1
-            parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, H, W, K, b_o, b_d, target,
-                                        rng_seed=nb.step_seed(0, tr_count[0]), chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
-        for _ in range(3):
-            step_train()
-        tr_steps = 5
-        tr_ms = timed(step_train, tr_steps)
-        train = {"value": n_batch * tr_steps / (tr_ms * 1e-3), "unit": "rays/s", "ms_per_step": tr_ms / tr_steps,
-                 "config": f"{n_batch}-ray batch, 64+128, perturb=1, raw_noise_std=1 (keyed Philox draws), MSE(rgb)+MSE(rgb0), Adam; "
-                           "forward + backward on bf16 tensor cores (recompute-with-save, data-gradient chain, split-K weight gradients)"}
+        def make_batch(n_batch):
+            sel = torch.randint(0, n_rays, (n_batch,), device=dev, generator=gen)
+            return (resident[0][0][sel].contiguous(), resident[0][1][sel].contiguous(),
+                    torch.rand((n_batch, 3), device=dev, generator=gen))
+
+        def train_leg(n_batch, what):
+            b_o, b_d, target = make_batch(n_batch)
+
+            def step_train():
+                # perturb / noise draws keyed by (seed, step, global ray index): the step does not depend on the number of GPUs
+                tr_count[0] += 1
+                parallel.train_step_sharded(nb.render, nb.img2mse, optim, bucket, H, W, K, b_o, b_d, target,
+                                            rng_seed=nb.step_seed(0, tr_count[0]), chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
+            for _ in range(3):
+                step_train()
+            tr_steps = 5
+            tr_ms = timed(step_train, tr_steps)
+            rate = n_batch * tr_steps / (tr_ms * 1e-3)
+            tflops = rate * TRAIN_FLOP_PER_RAY / 1e12
+            pk_ = peaks()
+            return {"value": rate, "unit": "rays/s", "ms_per_step": tr_ms / tr_steps, "rays_per_step": n_batch,
+                    "roofline": {"bound": "tensor", "achieved": tflops / world, "unit": "TFLOP/s per GPU", "peak": pk_["sustained"],
+                                 "frac": tflops / world / pk_["sustained"], "frac_of_burst_peak": tflops / world / pk_["burst"],
+                                 "flop_per_ray": TRAIN_FLOP_PER_RAY},
+                    "hbm_bytes_per_sample": train_traffic(),
+                    "config": f"{what}: {n_batch}-ray batch over {world} GPU(s), 64+128, perturb=1, raw_noise_std=1 (keyed Philox "
+                              "draws), MSE(rgb)+MSE(rgb0), Adam; forward + backward on bf16 tensor cores (forward-with-save, "
+                              "data-gradient chain, split-K weight gradients)"}
+        train = train_leg(4096 * world, "C2 x N (weak)")
+        if world > 1:
+            train_c4 = train_leg(32768, "C4 as stated (strong)")
+            # sharded step == single-GPU step on the same 32 768-ray batch: compare the reduced gradients with the gradients
+            # of the full batch computed on this GPU alone (fp32 accumulation-order tolerance)
+            b_o, b_d, target = make_batch(32768)
+            seed = nb.step_seed(0, 10 ** 6)
+            lo, hi, _ = parallel.shard_bounds(32768, world, rank, parallel.SHARD_ALIGN)
+            optim.zero_grad()
+            with nb.keyed_rng(seed, ray_offset=lo):
+                rgb, _, _, ex = nb.render(H, W, K, rays=(b_o[lo:hi], b_d[lo:hi]), chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
+            loss = (nb.img2mse(rgb, target[lo:hi]) + nb.img2mse(ex["rgb0"], target[lo:hi])) * ((hi - lo) / 32768)
+            loss.backward()
+            bucket.allreduce_sum()
+            g_sharded = bucket.flat.clone()
+            optim.zero_grad()
+            with nb.keyed_rng(seed, ray_offset=0):
+                rgb, _, _, ex = nb.render(H, W, K, rays=(b_o, b_d), chunk=args.chunk, near=NEAR, far=FAR, **kw_tr)
+            loss1 = nb.img2mse(rgb, target) + nb.img2mse(ex["rgb0"], target)
+            loss1.backward()
+            g_single = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in grad_vars])
+            rel = float((g_sharded - g_single).norm() / g_single.norm().clamp_min(1e-30))
+            worst = torch.tensor([rel], device=dev)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            train_sharded = {"grad_rel_err_vs_single_gpu": float(worst.item()), "equal_within_fp32_reorder": bool(worst.item() < 1e-4),
+                             "batch": 32768}
+            optim.zero_grad()
+
+    # ---- BASELINE configs[0] (C0): 100x100 Blender-shaped rays, N_samples=64, N_importance=0, no view directions,
+    # perturb=0 -- this repo's kernels (bf16 mode, output_linear head) next to the reference algorithm on the host CPU
+    c0 = None
+    if not args.no_c0 and rank == 0:
+        a0 = make_args(); a0.use_viewdirs = False; a0.N_importance = 0; a0.white_bkgd = False
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, kw0, _, _, _ = nb.create_nerf(a0, device=dev)
+        kw0["network_fn"].load_state_dict(SY.random_init_state_dict(100, use_viewdirs=False, input_ch_views=0, output_ch=4))
+        K0, c2w0 = SY.blender_shaped_camera(100, 100, 30.0)
+        ro0, rd0 = nb.get_rays(100, 100, K0, torch.from_numpy(c2w0).to(dev))
+        ro0, rd0 = ro0.reshape(-1, 3), rd0.reshape(-1, 3)
+
+        def step_c0():
+            nb.render(100, 100, K0, chunk=args.chunk, rays=(ro0, rd0), near=NEAR, far=FAR, **kw0)
+        with torch.no_grad():
+            for _ in range(3):
+                step_c0()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                step_c0()
+            e1.record()
+            torch.cuda.synchronize()
+        c0_ms = e0.elapsed_time(e1) / 20
+        c0 = {"gpu": {"value": 10000 / (c0_ms * 1e-3), "unit": "rays/s", "ms_per_frame": c0_ms, "dtype": "bf16",
+                      "tflops": 10000 / (c0_ms * 1e-3) * 64 * 984_064 / 1e12},
+              "config": "C0: 100x100 Blender-shaped rays (10000), N_samples=64, N_importance=0, no view directions, perturb=0, "
+                        "random-init 8x256 MLP (PCG64 seed 100); one launch of 1250 super-tiles: latency-, not throughput-sized"}
+        if not args.no_cpu_baseline:
+            r0, dt0, cores0 = cpu_reference_rate(10000, 3, 1, config="C0")
+            c0["cpu_reference"] = {"value": r0, "unit": "rays/s", "cores": cores0, "kind": "port", "s_per_frame": dt0,
+                                   "sample": "the full 10000-ray frame, oracle port on torch CPU fp32, 1 warm-up + 3 timed"}
 
     rays_per_step = n_rays * world
     value = rays_per_step * args.steps / (total_ms * 1e-3)
@@ -356,10 +502,11 @@ def main():
         line = {
             "metric": "rays/s (64+128 samples) render", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "vs_baseline_reason": VS_BASELINE_REASON, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step": rays_per_step, "chunk": args.chunk,
                        "parallelism": f"ray-sharded x{world}" if world > 1 else "single GPU",
-                       "l2": "working set per frame (2.6 GB raw/depth buffers) >> 126 MB L2, no flush needed",
+                       "l2": "working set per frame (depth / weight / record buffers of 20 chunks, fresh allocations cycled "
+                             "through the caching allocator) >> 126 MB L2, no flush needed",
                        "weights": "random init, numpy PCG64 seeds 0/1"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * n_rays * 12 * world,   # summed over ranks
                     "d2h_bytes_per_step": n_rays * 20 * world, "ms_per_step": e2e_ms / args.steps},
@@ -372,19 +519,29 @@ def main():
                          "frac_of_burst_peak": achieved / pk["burst"],
                          "kernel_share_of_step": tot_ms / total_ms, "launches_timed": len(mlp_times),
                          "whole_step_frac": value * FLOP_PER_RAY / 1e12 / world / peak},
+            "latency": latency,
         }
+        if sharded_equals_single is not None:
+            line["sharded_equals_single"] = sharded_equals_single
         if train is not None:
             line["train"] = train
+        if train_c4 is not None:
+            line["train_c4"] = train_c4
+        if train_sharded is not None:
+            line["train_sharded_equals_single"] = train_sharded
         if llff is not None:
             line["llff"] = llff
+        if c0 is not None:
+            line["c0"] = c0
         if world == 1 and not args.no_cpu_baseline:
-            n = 8192
+            n = REF_SAMPLE_RAYS
             rate, dt, cores = cpu_reference_rate(n, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"{n}-ray subset of the same frame (64+128, viewdirs), oracle port on "
-                                              f"torch CPU fp32 with {cores} threads, {dt:.1f} s"}
+                                              f"torch CPU fp32 with {cores} threads, 1 warm-up + 2 timed steps of {dt:.1f} s"}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -117,14 +117,28 @@ def watchdog_record():
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL).  Kernels are enqueued on the CURRENT device's current stream, so a
+    CUDA tensor on another device is refused instead of being dereferenced by the wrong GPU (the public entry points --
+    render, create_nerf's networks, train -- switch to the tensors' device themselves, see ``on_device``)."""
     if t is None:
         return None
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise NerfB200Error(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                            "wrap the call in `with torch.cuda.device(tensor.device):`")
     return t.data_ptr()
 
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(dev):
+    """Context manager: make ``dev`` (a torch.device or a CUDA tensor's device) the current CUDA device."""
+    import contextlib
+    dev = torch.device(dev)
+    if dev.type != "cuda":
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
 
 
 def require_cuda(*tensors):

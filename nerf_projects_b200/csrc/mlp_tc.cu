@@ -1118,10 +1118,13 @@ static int get_blob_maps(const void* blob, size_t bytes, BlobMaps* out) {   // r
 
 static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   static Sched sched_vd, sched_novd, sched_bwd, sched_bwd_novd;
-  static bool init = false;
+  static bool init[64] = {false};           // function attributes are per device
   static std::mutex mu;
+  int dev = 0;
+  NERFB_CUDA(cudaGetDevice(&dev));
+  NERFB_REQUIRE(dev >= 0 && dev < 64, "launch_mlp: device ordinal %d out of range", dev);
   std::unique_lock<std::mutex> lock(mu);
-  if (!init) {
+  if (!init[dev]) {
     build_schedule(true, sched_vd);
     build_schedule(false, sched_novd);
     build_schedule_bwd(true, sched_bwd);
@@ -1131,7 +1134,7 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    init = true;
+    init[dev] = true;
   }
   lock.unlock();
   a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
@@ -1149,10 +1152,13 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
   {  // parameter block -> constant bank, in stream order; launches on different streams are chained by an event
-    static cudaEvent_t last_done = nullptr;
-    static cudaStream_t last_stream = nullptr;
+    // (c_par, the event and the last stream are per device: every device has its own instance of the symbol)
+    static cudaEvent_t last_done_d[64] = {nullptr};
+    static cudaStream_t last_stream_d[64] = {nullptr};
     static std::mutex cmu;
     std::lock_guard<std::mutex> clock_(cmu);
+    cudaEvent_t& last_done = last_done_d[dev];
+    cudaStream_t& last_stream = last_stream_d[dev];
     const cudaStream_t st = as_stream(stream);
     if (last_done == nullptr) NERFB_CUDA(cudaEventCreateWithFlags(&last_done, cudaEventDisableTiming));
     else if (last_stream != st) NERFB_CUDA(cudaStreamWaitEvent(st, last_done, 0));

@@ -414,10 +414,13 @@ static int launch_wgrad(const char* who, long long nrows, int use_viewdirs, int 
   a.out_ch = out_ch;
   a.nstages = 8 * ((nrows + kSuperRows - 1) / kSuperRows);    // 4 tiles x 2 stages per 512-row super-tile
   a.watch = get_watch();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // function attributes are per device
+  int dev = 0;
+  NERFB_CUDA(cudaGetDevice(&dev));
+  NERFB_REQUIRE(dev >= 0 && dev < 64, "nerf_wgrad: device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
     NERFB_CUDA(cudaFuncSetAttribute(nerf_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   // deal the SMs to the jobs in proportion to their per-stage bytes (largest remainder), at least one each
   const int grid = sm_count() >= a.njobs ? sm_count() : a.njobs;

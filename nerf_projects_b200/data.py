@@ -52,14 +52,18 @@ class RayBatcher:
         self.images = torch.as_tensor(images, dtype=torch.float32).to(dev).contiguous()
         self.poses = torch.as_tensor(poses, dtype=torch.float32).to(dev).contiguous()
         n_img = self.images.shape[0]
-        self.i_train = torch.as_tensor(list(range(n_img)) if i_train is None else list(i_train), dtype=torch.int64,
-                                       device=dev)
+        self.i_train_host = [int(i) for i in (range(n_img) if i_train is None else i_train)]   # host copy: no device read per step
+        self.i_train = torch.as_tensor(self.i_train_host, dtype=torch.int64, device=dev)
         self.N_rand = int(N_rand)
         self.use_batching = bool(use_batching)
         self.precrop_iters, self.precrop_frac = int(precrop_iters), float(precrop_frac)
         self.gen = torch.Generator(device=dev)
+        # per-image mode draws the IMAGE index on the host (same seed -> same choice on every data-parallel rank) so that a
+        # step has no device->host read: only the pixel permutation stays on the device
+        self.host_gen = torch.Generator()
         if seed is not None:
             self.gen.manual_seed(seed)
+            self.host_gen.manual_seed(seed)
         self.dev = dev
         self._crop_ids = None
         self.epoch = 0
@@ -86,8 +90,8 @@ class RayBatcher:
 
     # ---- per-image sampling with the optional centre crop
     def _next_per_image(self, i: int):
-        k = int(torch.randint(0, self.i_train.numel(), (1,), device=self.dev, generator=self.gen))
-        img = int(self.i_train[k])
+        k = int(torch.randint(0, len(self.i_train_host), (1,), generator=self.host_gen))      # host draw: no sync
+        img = self.i_train_host[k]
         if i < self.precrop_iters:
             if self._crop_ids is None:
                 self._crop_ids = precrop_pixel_ids(self.H, self.W, self.precrop_frac).to(self.dev)

@@ -60,7 +60,8 @@ def get_rays(H, W, K, c2w):
         c2w = torch.as_tensor(np.asarray(c2w), dtype=torch.float32)
     if not c2w.is_cuda:
         c2w = c2w.cuda()
-    return ops.get_rays(int(H), int(W), K[0][0], K[1][1], K[0][2], K[1][2], c2w)
+    with L.on_device(c2w.device):
+        return ops.get_rays(int(H), int(W), K[0][0], K[1][1], K[0][2], K[1][2], c2w)
 
 
 def get_rays_np(H, W, K, c2w):
@@ -302,8 +303,14 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
 
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
-    """ipynb:558-640 -> [rgb_map, disp_map, acc_map, extras]."""
+    """ipynb:558-640 -> [rgb_map, disp_map, acc_map, extras].  Runs on the device of ``network_fn`` whatever the
+    current CUDA device is (the reference's ``.to(model_device)`` convention)."""
     dev = _device_of(kwargs)
+    with L.on_device(dev):
+        return _render(dev, H, W, K, chunk, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, kwargs)
+
+
+def _render(dev, H, W, K, chunk, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, kwargs):
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, K, _as_cuda(c2w, dev))
     else:
@@ -324,18 +331,40 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
 
 
+def _render_frame_sharded(H, W, K, chunk, c2w, render_kwargs, slot):
+    """One frame of render_path ray-sharded over all ranks of the default process group (parallel.render_sharded):
+    every rank renders its slice, one all-gather; every rank gets the full [H,W,3] / [H,W] maps."""
+    from . import parallel
+    dev = _device_of(render_kwargs)
+    rays_o, rays_d = get_rays(H, W, K, _as_cuda(c2w, dev))
+    frame = parallel.render_sharded(render, H, W, K, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), chunk=chunk, slot=slot,
+                                    async_gather=True, **render_kwargs)
+    rgb, disp, acc = frame.maps()
+    # own storage: the gather buffer of this slot is reused two frames later, the D2H copy may still be reading
+    return rgb.reshape(H, W, 3).contiguous(), disp.reshape(H, W).contiguous(), acc.reshape(H, W).contiguous()
+
+
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
-                calculate_metrics=False, metrics_include_lpips=True, metrics_device="cuda"):
+                calculate_metrics=False, metrics_include_lpips=True, metrics_device="cuda", sharded=None):
     """ipynb:650-758.  The device->host copy of frame k overlaps the render of
     frame k+1 (pinned buffers + a copy stream).  With ``calculate_metrics`` and
     ``gt_imgs``, MSE / PSNR / SSIM of every frame are computed on the GPU from the
     frame where it lies (metrics.image_metrics, one fused pass, no host sync inside
     the loop) and averaged like the reference: ``avg_/std_{psnr,ssim,mse[,lpips]}``.
-    LPIPS needs the optional ``lpips`` package (skipped with a warning otherwise)."""
+    LPIPS needs the optional ``lpips`` package (skipped with a warning otherwise).
+
+    ``sharded`` (default: automatically, when a torch.distributed group with more than one rank is initialised): every
+    frame is ray-sharded over all ranks -- all ranks must call render_path with the same poses; every rank returns the
+    full frames, only rank 0 writes files to ``savedir``."""
+    import torch.distributed as dist
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
     dev = _device_of(render_kwargs)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    sharded = multi if sharded is None else (bool(sharded) and multi)
+    if sharded and dist.get_rank() != 0:
+        savedir = None
     n = len(render_poses)
     rgbs = np.empty((n, H, W, 3), np.float32)
     disps = np.empty((n, H, W), np.float32)
@@ -361,7 +390,10 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
     t = time.time()
     for i, c2w in enumerate(render_poses):
         t = time.time()
-        rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
+        if sharded:
+            rgb, disp, acc = _render_frame_sharded(H, W, K, chunk, c2w[:3, :4], render_kwargs, slot=i % 2)
+        else:
+            rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
         if calculate_metrics and gt_imgs is not None and render_factor == 0 and i < len(gt_imgs):
             gt = torch.as_tensor(np.asarray(gt_imgs[i]), dtype=torch.float32, device=dev)[..., :3]
             frame_metrics.append(M.image_metrics(rgb, gt)[0])

@@ -104,6 +104,13 @@ def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
 
     render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer = create_nerf(args, device=device)
     dev = next(render_kwargs_train["network_fn"].parameters()).device
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        # data parallel all-reduces gradients only: make every replica (weights, Adam state, lr, resume step) rank 0's,
+        # whatever each rank's RNG state was before create_nerf and whichever rank could see the checkpoint
+        parallel.broadcast_parameters(grad_vars, optimizer)
+        step0 = torch.tensor([start], dtype=torch.int64, device=dev)
+        dist.broadcast(step0, src=0)
+        start = int(step0.item())
     for kw in (render_kwargs_train, render_kwargs_test):
         kw.update(near=near, far=far)
     global_step = start
@@ -112,16 +119,22 @@ def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
     images = np.asarray(images, dtype=np.float32)
     poses_t = torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(dev)
 
+    is_rank0 = not dist.is_initialized() or dist.get_rank() == 0
+
     def testset(i, tag):
+        """Test-set render (ipynb:1312-1385).  Under torch.distributed every frame is ray-sharded over ALL ranks
+        (render_path(sharded=...) default); rank 0 alone writes the frames and metrics.json."""
         savedir = os.path.join(args.basedir, args.expname, f"{tag}_{i:06d}")
-        os.makedirs(savedir, exist_ok=True)
+        if is_rank0:
+            os.makedirs(savedir, exist_ok=True)
         with torch.no_grad():
             out = render_path(poses_t[list(i_test)], hwf, K, chunk, render_kwargs_test, gt_imgs=images[list(i_test)],
-                              savedir=savedir, calculate_metrics=True, metrics_include_lpips=False,
+                              savedir=savedir if is_rank0 else None, calculate_metrics=True, metrics_include_lpips=False,
                               render_factor=_get(args, "render_factor", 0))
         metrics = out[2] if len(out) > 2 else {}
-        with open(os.path.join(savedir, "metrics.json"), "w") as f:
-            json.dump({"iteration": i, "metrics": metrics}, f, indent=2)
+        if is_rank0:
+            with open(os.path.join(savedir, "metrics.json"), "w") as f:
+                json.dump({"iteration": i, "metrics": metrics}, f, indent=2)
         return metrics
 
     if _get(args, "render_only", False):                       # ipynb:1142-1165
@@ -174,14 +187,16 @@ def train(args, data=None, N_iters=200000 + 1, device=None, log=print):
             path = os.path.join(args.basedir, args.expname, "checkpoints", f"{i:06d}.tar")
             save_checkpoint(path, global_step, render_kwargs_train, optimizer)
             log("Saved checkpoints at", path)
-        if i % i_video == 0 and i > 0 and (not dist.is_initialized() or dist.get_rank() == 0):
-            # validation trajectory (ipynb:1301-1310); frames are kept as arrays (MP4 writing needs imageio-ffmpeg)
+        if i % i_video == 0 and i > 0:
+            # validation trajectory (ipynb:1301-1310), ray-sharded over all ranks; rank 0 keeps the frames as arrays (MP4
+            # writing needs imageio-ffmpeg)
             with torch.no_grad():
                 rgbs, disps = render_path(render_poses, hwf, K, chunk, render_kwargs_test)[:2]
-            base = os.path.join(args.basedir, args.expname, "{}_spiral_{:06d}_".format(args.expname, i))
-            np.save(base + "rgb.npy", (255 * np.clip(rgbs, 0, 1)).astype(np.uint8))
-            np.save(base + "disp.npy", (255 * np.clip(disps / max(float(np.max(disps)), 1e-10), 0, 1)).astype(np.uint8))
-            log("Done, saving", rgbs.shape, disps.shape)
+            if is_rank0:
+                base = os.path.join(args.basedir, args.expname, "{}_spiral_{:06d}_".format(args.expname, i))
+                np.save(base + "rgb.npy", (255 * np.clip(rgbs, 0, 1)).astype(np.uint8))
+                np.save(base + "disp.npy", (255 * np.clip(disps / max(float(np.max(disps)), 1e-10), 0, 1)).astype(np.uint8))
+                log("Done, saving", rgbs.shape, disps.shape)
         if i % i_testset == 0 and i > 0 and len(i_test) > 0:
             test_metrics[i] = testset(i, "testset")
             log(f"[TEST] Iter: {i} " + " ".join(f"{k}: {v:.4f}" for k, v in test_metrics[i].items()))

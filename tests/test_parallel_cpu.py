@@ -115,3 +115,100 @@ def test_render_sharded_and_grad_bucket_gloo_world2(n):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, out), nprocs=world, join=True)
     assert dict(out) == {0: 3, 1: 3}
+
+
+def test_shard_bounds_alignment():
+    """Shards are whole multiples of SHARD_ALIGN rays (whole super-tiles of the fused kernel); only the tail is ragged."""
+    from nerf_projects_b200.parallel import SHARD_ALIGN, shard_bounds
+    for n in (640000, 762048, 32768, 4097, 5):
+        for world in (2, 3, 8):
+            spans = [shard_bounds(n, world, r, SHARD_ALIGN) for r in range(world)]
+            assert all(per % SHARD_ALIGN == 0 for _, _, per in spans)
+            assert sum(hi - lo for lo, hi, _ in spans) == n
+            assert all((hi - lo) % SHARD_ALIGN == 0 for lo, hi, _ in spans if hi < n)
+
+
+class _TinyModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.lin = torch.nn.Linear(6, 3)
+
+
+def _model_render(model):
+    def render(H, W, K, rays=None, **kw):
+        ro, rd = rays
+        rgb = torch.tanh(model.lin(torch.cat([ro, rd], -1)))
+        return [rgb, rgb[:, 0], rgb[:, 1], {"rgb0": rgb * 0.5}]
+    return render
+
+
+def _worker_train(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nerf_projects_b200 import parallel
+        mse = lambda x, y: torch.mean((x - y) ** 2)
+        g = torch.Generator().manual_seed(1)
+        ro, rd, tgt = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.rand(n, 3, generator=g)
+        # replicas that start DIFFERENT (a per-rank seed): broadcast_parameters makes them rank 0's
+        model = _TinyModel()
+        with torch.no_grad():
+            model.lin.weight.add_(float(rank))
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        parallel.broadcast_parameters(list(model.parameters()), opt)
+        ref = _TinyModel()
+        ok_bcast = all(torch.equal(a, b) for a, b in zip(model.parameters(), ref.parameters()))
+        # single-process reference step on the GLOBAL batch
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+        r_rgb = _model_render(ref)(0, 0, None, rays=(ro, rd))
+        r_loss = mse(r_rgb[0], tgt) + mse(r_rgb[3]["rgb0"], tgt)
+        ropt.zero_grad(); r_loss.backward(); ropt.step()
+        bucket = parallel.GradBucket(list(model.parameters()))
+        loss = parallel.train_step_sharded(_model_render(model), mse, opt, bucket, 0, 0, None, ro, rd, tgt)
+        ok_loss = abs(float(loss) - float(r_loss)) < 1e-6
+        ok_step = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(model.parameters(), ref.parameters()))
+        out[rank] = int(ok_bcast) + 2 * int(ok_loss) + 4 * int(ok_step)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1, 9, 16, 37])
+def test_train_step_sharded_equals_global_batch_step_gloo_world2(n):
+    """the data-parallel step must equal the single-process step on the global batch for uneven shards
+    (n % world != 0; 9 and 37 rays also leave the aligned split ragged) and when a rank gets NO rays (n = 1: the short
+    last batch of an epoch) -- that rank joins the all-reduce with zero gradients instead of raising / hanging.
+    Replicas that start different are synchronised by broadcast_parameters."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_train, args=(2, port, n, out), nprocs=2, join=True)
+    assert dict(out) == {0: 7, 1: 7}
+
+
+def _worker_async(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nerf_projects_b200 import parallel
+        g = torch.Generator().manual_seed(0)
+        frames = [(torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)) for _ in range(3)]
+        handles = [parallel.render_sharded(_fake_render, 4, 4, None, ro, rd, async_gather=True, slot=i % 2)
+                   for i, (ro, rd) in enumerate(frames[:2])]
+        ok = True
+        for (ro, rd), h in zip(frames[:2], handles):          # two gathers in flight, two buffer slots
+            rgb, disp, acc = h.maps()
+            ok &= torch.equal(rgb, ro * 2.0 + rd) and torch.equal(disp, ro[:, 0] + 1.0) and torch.equal(acc, rd[:, 2] * 3)
+        packed = parallel.render_sharded(_fake_render, 4, 4, None, *frames[2], return_packed=True)
+        ok &= packed.shape == (n, 5) and torch.equal(packed[:, 0:3], frames[2][0] * 2.0 + frames[2][1])
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_sharded_async_gather_gloo_world2():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_async, args=(2, port, 21, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
