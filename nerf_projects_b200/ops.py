@@ -130,7 +130,9 @@ def embed_samples(R, S, rays, z, pts, viewdirs, Lp, Lv, enc, col_pts, enc_dir, c
 
 def _ld(t):
     assert t.stride(-1) == 1 or t.shape[-1] == 1, "innermost dimension must be contiguous"
-    return t.stride(0) if t.dim() == 2 else t.shape[-1]
+    if t.dim() != 2 or t.shape[0] == 1:      # a single row: its stride is arbitrary (numpy transposes give 1), any ld >= width works
+        return t.shape[-1]
+    return t.stride(0)
 
 
 def linear_fwd(X, W, b, Y, relu: bool, K: Optional[int] = None):
