@@ -134,14 +134,14 @@ def test_c2_batch_forward_slice_matches_reference():
 def test_discontinuity_gate_logic():
     """oracle/discontinuity.py: the gate accepts errors beyond tol only inside the explained set and only for a few rays."""
     from oracle import discontinuity as DS
-    err = torch.tensor([1e-5] * 198 + [0.5, 0.5])
-    explained = torch.zeros(200, dtype=torch.bool); explained[-2:] = True
-    DS.gate(err, 1e-4, explained, "ok")
+    err = torch.tensor([1e-5] * 598 + [0.5, 0.5])
+    explained = torch.zeros(600, dtype=torch.bool); explained[-2:] = True
+    DS.gate(err, 1e-4, explained, "ok")                       # 2 of 600 <= 0.5 %, both explained
     with pytest.raises(AssertionError):
-        DS.gate(err, 1e-4, torch.zeros(200, dtype=torch.bool), "unexplained outliers")
-    many = torch.tensor([1e-5] * 180 + [0.5] * 20)
+        DS.gate(err, 1e-4, torch.zeros(600, dtype=torch.bool), "unexplained outliers")
+    many = torch.tensor([1e-5] * 590 + [0.5] * 10)
     with pytest.raises(AssertionError):
-        DS.gate(many, 1e-4, torch.ones(200, dtype=torch.bool), "too many outliers even if explained")
+        DS.gate(many, 1e-4, torch.ones(600, dtype=torch.bool), "too many outliers even if explained")
     # fp32 mode never excludes rays for sigma_last
     raw = torch.zeros(4, 8, 4)
     assert not DS.sigma_last_set(raw, "fp32").any() and DS.sigma_last_set(raw, "bf16").all()
