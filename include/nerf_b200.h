@@ -193,6 +193,27 @@ int nerfb_pack_weights(const float* const* h_params, int use_viewdirs, int out_c
 int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width, const float* z,
                        const float* pts, const float* viewdirs, int use_viewdirs, int out_ch,
                        const void* packed, float* raw, void* stream);
+/* Inference: the same network pass WITH the alpha compositing of raw2outputs (ipynb:254-349) folded in -- the
+ * per-sample [rgb, sigma] never leave the SM (north_star (1)).  S must be a multiple of 32: each warp-sized segment of a
+ * ray is composited where it was evaluated (fp32 prefix product of 1 - alpha + 1e-10 inside the segment; bf16 mode) and leaves a
+ * 32-byte record in `rec` [R][S/32][8 floats] = {Q = product over the segment, unused, sums of w', w' r, w' g, w' b,
+ * w' z, unused}; the transmittance in front of a segment is the product of the earlier records' Q.  z [R,S] or NULL: coarse
+ * depths near*(1-t)+far*t (lindisp: the disparity-linear form) are computed in-kernel from columns 6/7 of `rays`
+ * (ipynb:418-425).  wpart [R,S] or NULL: the per-sample partial weights w' (coarse pass: nerfb_resample_records needs
+ * them).  A ray is finished by nerfb_composite_finish (final pass) or nerfb_resample_records (coarse pass). */
+int nerfb_mlp_fwd_composite_bf16(int R, int S, const float* rays, int ray_width, const float* z, int lindisp,
+                                 int use_viewdirs, int out_ch, const void* packed, float* rec, float* wpart, void* stream);
+/* rgb [R,3], disp / acc / depth [R] (NULL to skip) of raw2outputs from the nseg = S/32 records of every ray. */
+int nerfb_composite_finish(int R, int nseg, const float* rec, int white_bkgd, float* rgb, float* disp, float* acc,
+                           float* depth, void* stream);
+/* Second launch of the fused coarse pass (ipynb:451-467): finishes the coarse maps rgb0 / disp0 / acc0 / depth0 from
+ * the records, rebuilds the coarse weights (kept in shared memory) and runs z_mid / sample_pdf(weights[1:-1]) /
+ * sort(cat) / z_std exactly like nerfb_hierarchical_z.  z NULL: coarse depths recomputed from the rays as above.
+ * z_out [R,S+N]; z_samples [R,N] or NULL; z_std [R] or NULL. */
+int nerfb_resample_records(int R, int S, int N, const float* rays, int ray_width, const float* z, int lindisp,
+                           const float* wpart, const float* rec, int white_bkgd, int det, const float* u, float* rgb,
+                           float* disp, float* acc, float* depth, float* z_out, float* z_samples, float* z_std,
+                           void* stream);
 /* ---- training: parameter gradients of the MLP on tensor cores (replaces the autograd graph of
  * NeRF.forward, nerf.py:57-111, under loss.backward(), ipynb:1274).  These three are for use_viewdirs networks;
  * the *_nv_* variants below cover use_viewdirs=False.

@@ -44,6 +44,9 @@ _SIGS = {
     "nerfb_packed_weights_bytes": ([_i], C.c_size_t),
     "nerfb_pack_weights": ([C.POINTER(_vp), _i, _i, _vp, _vp], _i),
     "nerfb_mlp_fwd_bf16": ([_i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
+    "nerfb_mlp_fwd_composite_bf16": ([_i, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_composite_finish": ([_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "nerfb_resample_records": ([_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_train_store_bytes": ([_ll, _i], C.c_size_t),
     "nerfb_mlp_fwd_save_bf16": ([_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_packed_weights_bwd_bytes": ([], C.c_size_t),

@@ -53,4 +53,12 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   return __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
 }
 
+// coarse sample depth i of S between near and far (ipynb:418-425), the exact operations of coarse_z_kernel
+__device__ __forceinline__ float z_at(int i, int S, float near_v, float far_v, int lindisp) {
+  const float t = linspace01(i, S);
+  const float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near_v, omt), __fmul_rn(far_v, t));
+  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near_v), omt), __fmul_rn(__fdiv_rn(1.0f, far_v), t)));
+}
+
 }  // namespace nerfb

@@ -313,6 +313,35 @@ raw2outputs_bwd_regs_kernel(int R, int S, const float* __restrict__ raw, const f
   }
 }
 
+// Finish of the rays whose segments nerf_mlp_kernel<FWD_COMP> composited (mlp_tc.cu: composite_tile): one thread per
+// ray walks the ray's nseg records {Q, -, sum w', sum w' r, g, b, sum w' z, -} in order, carrying the
+// transmittance T = product of the earlier Q in fp64 like torch.cumprod's running product, and writes the maps of
+// raw2outputs (ipynb:332-347).  32 bytes per 32 samples are read: 1 byte per sample instead of the 20 of raw + z.
+__global__ void __launch_bounds__(128)
+composite_finish_kernel(int R, int nseg, const float* __restrict__ rec, int white, float* __restrict__ rgb,
+                        float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ depth) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float4* q = reinterpret_cast<const float4*>(rec + (size_t)r * nseg * 8);
+  double T = 1.0;
+  float asum = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, dsum = 0.f;
+  for (int s = 0; s < nseg; ++s) {
+    const float4 ra = __ldg(q + 2 * s), rb = __ldg(q + 2 * s + 1);
+    const float Tf = (float)T;
+    asum = fmaf(Tf, ra.z, asum); c0 = fmaf(Tf, ra.w, c0); c1 = fmaf(Tf, rb.x, c1); c2 = fmaf(Tf, rb.y, c2);
+    dsum = fmaf(Tf, rb.z, dsum);
+    T *= (double)ra.x;
+  }
+  if (white) {
+    const float bg = __fsub_rn(1.0f, asum);
+    c0 += bg; c1 += bg; c2 += bg;
+  }
+  rgb[3 * r + 0] = c0; rgb[3 * r + 1] = c1; rgb[3 * r + 2] = c2;
+  if (depth) depth[r] = dsum;
+  if (acc) acc[r] = asum;
+  if (disp) disp[r] = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(dsum, fmaxf(1e-10f, asum)), 1e-10f));
+}
+
 // NCH for the register-resident kernels, or 0 when they do not apply
 inline int regs_nch(int S, int raw_ch, const void* raw, const void* out) {
   if (raw_ch != 4 || !aligned16(raw) || !aligned16(out) || S > 256) return 0;
@@ -347,6 +376,14 @@ extern "C" int nerfb_raw2outputs_fwd(int R, int S, const float* raw, int raw_ch,
   }
 #undef NERFB_FWD_REGS
   return check_launch("raw2outputs_fwd_kernel");
+}
+
+extern "C" int nerfb_composite_finish(int R, int nseg, const float* rec, int white_bkgd, float* rgb, float* disp, float* acc,
+                                      float* depth, void* stream) {
+  NERFB_REQUIRE(R >= 0 && nseg >= 1 && nseg <= 32 && rec && rgb && aligned16(rec), "nerfb_composite_finish: bad arguments");
+  if (R == 0) return NERFB_OK;
+  composite_finish_kernel<<<cdiv(R, 128), 128, 0, as_stream(stream)>>>(R, nseg, rec, white_bkgd, rgb, disp, acc, depth);
+  return check_launch("composite_finish_kernel");
 }
 
 extern "C" int nerfb_raw2outputs_bwd(int R, int S, const float* raw, int raw_ch, const float* z,

@@ -42,7 +42,7 @@ constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
 constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
 constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
 constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
-constexpr int kNumBars = 2 * kNS + 2 + 2 + 1;           // w_full, w_empty, act_ready[2], mma_done[2], enc_free
+constexpr int kNumBars = 2 * kNS + 2 + 2 + 1 + 4;       // w_full, w_empty, act_ready[2], mma_done[2], enc_free, stage_full[2], stage_free[2]
 constexpr int kSmTmemSlot = kSmBars + kNumBars * 8;
 constexpr int kSmOps = kSmTmemSlot + 16;                 // copy of Sched::ops (u32 each)
 constexpr int kSmLoads = kSmOps + 84 * 4;                // copy of Sched::loads (2 x u32 each)
@@ -75,6 +75,10 @@ constexpr int kNumBwdChunks = 34;                     // views^T(2) feat^T(4) L7
 constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
 // *_NV: the network without view directions (output_linear head) -- separate instantiations, so the view-dependent
 // training kernels compile exactly as before
-enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2, MODE_FWD_SAVE_NV = 3, MODE_BWD_NV = 4 };
+// MODE_FWD_COMP: the forward with the alpha compositing of raw2outputs folded in (inference): raw is never written
+enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2, MODE_FWD_SAVE_NV = 3, MODE_BWD_NV = 4, MODE_FWD_COMP = 5 };
+// compositing records: per ray and 32-sample segment 8 floats = {Q = product of 1-alpha+1e-10 over the segment, unused,
+// sum w', sum w' r, sum w' g, sum w' b, sum w' z, unused} with w' = alpha * (exclusive product inside the segment)
+constexpr int kRecFloats = 8;
 
 }  // namespace nerfb

@@ -36,6 +36,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include "mlp_layout.cuh"
+#include "composite.cuh"
 
 namespace nerfb {
 using namespace tc05;
@@ -163,6 +164,11 @@ struct MlpArgs {
   const float* d_raw; // MODE_BWD: [nrows,4]
   const float* d_raw4; // MODE_BWD without view directions: gradient of output channel 4 [nrows] or null
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
+  // MODE_FWD_COMP: compositing folded into the forward
+  int lindisp;        // z == nullptr: coarse depths computed in-kernel from the rays' near / far (z_at)
+  float zstep;        // fl(1 / (S - 1)): torch.linspace's step for those depths
+  float* comp_rec;    // [R][S/32][kRecFloats] segment records
+  float* comp_wpart;  // [R*S] alpha * (exclusive product inside the segment), or null (final pass)
 };
 constexpr int kTraceLen = 4096;
 
@@ -257,6 +263,91 @@ __device__ __forceinline__ void rgb_head_half(const uint32_t (&v)[32], int b, fl
   signbits = m;
 }
 
+// ------------------------------------------------- compositing (MODE_FWD_COMP)
+// raw2outputs (ipynb:254-349) folded into the forward: a warp composites the 32 consecutive samples of ONE ray (S is a
+// multiple of 32) whose [rgb logits, sigma] the final epilogue has left in shared memory.  Inside the segment: alpha, the
+// exclusive product P_i of (1 - alpha + 1e-10), w'_i = alpha_i * P_i, and the sums of w', w' rgb, w' z; the segment's
+// record {Q = product over the segment, sums} goes to global memory (32 bytes per 32 samples).  The transmittance in
+// front of a segment, T = product of the earlier segments' Q, multiplies the sums when the ray is finished:
+// nerfb_composite_finish (final pass) or nerfb_resample_records (coarse pass, which also needs the weights T * w').
+//
+// WHO does it: two otherwise idle warps per CTA (warp 3: tile 0, warp 2: tile 1), fed through a 4 KB stage in shared
+// memory that the final epilogue fills, and started only inside the next super-tile's middle layers.  The fused kernel
+// is bound by the instruction issue of its eight epilogue warps (ncu source page: they wait for the tensor pipe in only
+// ~7 % of their samples), so every instruction added on an SM scheduler costs throughput -- measured A/B
+// (profiles/README.md): one compositor warp -2.0 % of the kernel (stubbing its body out gave it all back; an unrolled
+// IEEE / fp64 body and a rolled fp32 one cost the same), the same work inside the epilogue warps -3.5 %, spread over
+// three of their layers -4 %; a last-arriver finish inside the kernel (arrival counters, __threadfence) ~4 k cycles per
+// segment.  Hence: a small rolled fp32 loop with the fast exp (MUFU) forms, on two schedulers.  This path exists in
+// bf16 mode only, whose tolerance (2e-2) is five orders of magnitude above these rounding differences; the fp64-scan
+// kernels (composite.cu) remain the validation-mode / training path.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float z_at_step(int i, int S, float step, float near_v, float far_v, int lindisp) {
+  // z_at (common.cuh) with torch.linspace's step = fl(1/(S-1)) precomputed on the host: bit-identical depths
+  const float t = (S <= 1) ? 0.f : (i < S / 2 ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(S - 1 - i), 1.0f));
+  const float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near_v, omt), __fmul_rn(far_v, t));
+  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near_v), omt), __fmul_rn(__fdiv_rn(1.0f, far_v), t)));
+}
+
+// the four 32-sample segments of one 128-row tile; g0 = global index of the tile's first sample
+__device__ __noinline__ void composite_tile(const MlpArgs& a, const float4* __restrict__ stage, long long g0, int lane) {
+  const int S = a.S;
+  if (g0 >= a.nrows) return;                  // warp-uniform (nrows = R*S is a multiple of 32)
+  uint32_t r = (uint32_t)g0 / (uint32_t)S;    // COMP launches are limited to < 2^31 samples
+  int i0 = (int)((uint32_t)g0 - r * (uint32_t)S);
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const long long grow0 = g0 + 32 * q;
+    if (grow0 >= a.nrows) return;
+    const float4 v = stage[32 * q + lane];
+    const float* rp = a.rays + (size_t)r * a.rw;
+    const bool last_seg = (i0 + 32 == S);
+    float zi, zl = 0.f;
+    if (a.z != nullptr) {
+      zi = __ldg(a.z + grow0 + lane);
+      if (!last_seg) zl = __ldg(a.z + grow0 + 32);                   // first depth of the ray's next segment
+    } else {
+      const float near_v = __ldg(rp + 6), far_v = __ldg(rp + 7);
+      zi = z_at_step(i0 + lane, S, a.zstep, near_v, far_v, a.lindisp);
+      if (!last_seg) zl = z_at_step(i0 + 32, S, a.zstep, near_v, far_v, a.lindisp);
+    }
+    const float nrm = ray_norm(rp + 3);
+    float zn = __shfl_down_sync(0xffffffffu, zi, 1);
+    if (lane == 31) zn = zl;
+    const float dist = ((lane == 31 && last_seg) ? 1e10f : (zn - zi)) * nrm;
+    const float alpha = 1.0f - __expf(-fmaxf(v.w, 0.f) * dist);
+    float p = (1.0f - alpha) + 1e-10f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float pq = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) p *= pq;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.0f;
+    const float Q = __shfl_sync(0xffffffffu, p, 31);
+    const float pw = alpha * excl;
+    if (a.comp_wpart != nullptr) a.comp_wpart[grow0 + lane] = pw;
+    float A = pw, C0 = pw * fast_sigmoid(v.x), C1 = pw * fast_sigmoid(v.y), C2 = pw * fast_sigmoid(v.z), D = pw * zi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      A += __shfl_xor_sync(0xffffffffu, A, o);
+      C0 += __shfl_xor_sync(0xffffffffu, C0, o);
+      C1 += __shfl_xor_sync(0xffffffffu, C1, o);
+      C2 += __shfl_xor_sync(0xffffffffu, C2, o);
+      D += __shfl_xor_sync(0xffffffffu, D, o);
+    }
+    if (lane == 0) {
+      float4* rq = reinterpret_cast<float4*>(a.comp_rec + ((size_t)r * (S >> 5) + (i0 >> 5)) * kRecFloats);
+      rq[0] = make_float4(Q, 0.f, A, C0);
+      rq[1] = make_float4(C1, C2, D, 0.f);
+    }
+    i0 += 32;
+    if (i0 == S) { i0 = 0; ++r; }
+  }
+}
+
 // -------------------------------------------------------------- kernel
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -265,6 +356,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   constexpr bool SAVE = (MODE == MODE_FWD_SAVE || MODE == MODE_FWD_SAVE_NV);
   constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_BWD_NV);
   constexpr bool NV = (MODE == MODE_FWD_SAVE_NV || MODE == MODE_BWD_NV);   // training kernels of the no-view-directions network
+  constexpr bool COMP = (MODE == MODE_FWD_COMP);                            // forward + compositing (inference)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -275,6 +367,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
   float* s_sig = reinterpret_cast<float*>(smem + kSmSig);
   auto bar = [&](int i) -> uint32_t { return sbase + kSmBars + 8 * i; };
   const int B_FULL = 0, B_EMPTY = kNS, B_ACT = 2 * kNS, B_DONE = 2 * kNS + 2, B_ENC = 2 * kNS + 4;
+  const int B_STFULL = 2 * kNS + 5, B_STFREE = 2 * kNS + 7;      // MODE_FWD_COMP: [rgb, sigma] stage of tile t published / consumed
 
   if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xA11, sbase, 0);
   // debug timeline: blocks 0 (leader) and 1 (peer) of cluster 0; 4 regions each: loader, MMA, epilogue, relay/observer
@@ -298,6 +391,10 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     mbar_init(bar(B_DONE + 0), 1);
     mbar_init(bar(B_DONE + 1), 1);
     mbar_init(bar(B_ENC), 1);
+    mbar_init(bar(B_STFULL + 0), 1);
+    mbar_init(bar(B_STFULL + 1), 1);
+    mbar_init(bar(B_STFREE + 0), 1);
+    mbar_init(bar(B_STFREE + 1), 1);
     fence_barrier_init();
   }
   // The schedule tables are read from SHARED memory in the hot loops: a dynamically indexed read of the
@@ -346,6 +443,20 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           tr(0, 0xA00 + q);
         }
       }
+    }
+  } else if (COMP && (warp == 3 || warp == 2)) {
+    // ===================== compositors: warp 3 takes tile 0, warp 2 tile 1 (two SM schedulers share the cost); each
+    // consumes the [rgb logits, sigma] stage of its tile once the epilogue publishes it
+    const int t = 3 - warp;
+    const bool vdc = a.use_viewdirs != 0;
+    const float4* stage = (vdc ? reinterpret_cast<const float4*>(s_par + kOffHeadW + 256)
+                               : reinterpret_cast<const float4*>(smem + kSmEnc + 8192)) + t * 128;
+    for (int it = 0; it < niter; ++it) {
+      const long long st = cluster_id + (long long)it * a.nclusters;
+      mbar_wait(bar(B_STFULL + t), (uint32_t)(it & 1), a.watch, 0xC00 + t);
+      composite_tile(a, stage, st * kSuperRows + rank * kTileRows + 2 * t * kTileRows, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_STFREE + t));
     }
   } else if (warp == 3) {
     // ===================== (idle; debug observer of the leader's weight barriers when tracing)
@@ -487,7 +598,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         } else {
           const long long r = grow / a.S;
           const float* ray = a.rays + r * a.rw;
-          const float zz = __ldg(a.z + grow);
+          const float zz = (COMP && a.z == nullptr)
+                               ? z_at_step((int)(grow - r * a.S), a.S, a.zstep, __ldg(ray + 6), __ldg(ray + 7), a.lindisp)
+                               : __ldg(a.z + grow);
 #pragma unroll
           for (int j = 0; j < 3; ++j) p[j] = __fadd_rn(__ldg(ray + j), __fmul_rn(__ldg(ray + 3 + j), zz));
         }
@@ -668,6 +781,20 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                 for (int k = 0; k < 5; ++k) part[k] = fmaf(x, s_par[kOffHeadW + 256 * k + 128 * hh + 32 * b + j], part[k]);
               }
             }
+            if constexpr (COMP) {
+              // enc buffer (idle until the next super-tile's skip layer): bytes 0..4095 = the hh == 1 partial sums
+              // [tile][row] float4, bytes 8192..12287 = the stage [tile][row] float4 the compositor warp reads
+              float4* xch = reinterpret_cast<float4*>(smem + kSmEnc) + (t * 128 + row);
+              float4* stg = reinterpret_cast<float4*>(smem + kSmEnc + 8192) + (t * 128 + row);
+              if (it > 0) mbar_wait(bar(B_STFREE + t), (uint32_t)((it - 1) & 1), a.watch, 0xC10 + t);
+              if (hh == 1) *xch = make_float4(part[0], part[1], part[2], part[3]);
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (hh == 0) {
+                const float4 o = *xch;
+                *stg = make_float4(part[0] + o.x + s_par[kOffHeadB + 0], part[1] + o.y + s_par[kOffHeadB + 1],
+                                   part[2] + o.z + s_par[kOffHeadB + 2], part[3] + o.w + s_par[kOffHeadB + 3]);
+              }
+            } else {
             // exchange the two column halves through the (idle) enc buffer: [tile][half][row][8]
             float* xch = reinterpret_cast<float*>(smem + kSmEnc);
 #pragma unroll
@@ -677,6 +804,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               for (int k = 0; k < a.out_ch; ++k)
                 a.raw[grow[t] * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
                                                 xch[((t * 2 + 1) * 128 + row) * 8 + k] + s_par[kOffHeadB + k];
+            }
             }
           } else {
             // ---- l == 9: view layer epilogue + rgb head -> raw.  Both column halves work: thread (row, hh) takes
@@ -707,6 +835,20 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               if (SAVE)
                 *reinterpret_cast<uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes + 8 * hh) =
                     make_uint2(sbits[0], sbits[1]);
+              if constexpr (COMP) {
+                // stage [tile][row] float4 in the unused output_linear rows of the parameter block: the hh == 1 partial
+                // sums cross over through it, then it holds the sample's [rgb logits, sigma] for the compositor warp
+                float4* stg = reinterpret_cast<float4*>(s_par + kOffHeadW + 256) + (t * 128 + row);
+                if (it > 0) mbar_wait(bar(B_STFREE + t), (uint32_t)((it - 1) & 1), a.watch, 0xC10 + t);
+                if (hh == 1) *stg = make_float4(c0, c1, c2, 0.f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (hh == 0) {
+                  const float4 o = *stg;
+                  const float sigma = s_sig[(t * 2 + 0) * 128 + row] + s_sig[(t * 2 + 1) * 128 + row] + s_par[kOffHeadB];
+                  *stg = make_float4(c0 + o.x + s_par[kOffRgbB], c1 + o.y + s_par[kOffRgbB + 1],
+                                     c2 + o.z + s_par[kOffRgbB + 2], sigma);
+                }
+              } else {
               float* xch = s_par + kOffHeadW + 256 + (t * 128 + row) * 3;
               if (hh == 1) { xch[0] = c0; xch[1] = c1; xch[2] = c2; }
               asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -716,10 +858,17 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
                     make_float4(c0 + xch[0] + s_par[kOffRgbB], c1 + xch[1] + s_par[kOffRgbB + 1],
                                 c2 + xch[2] + s_par[kOffRgbB + 2], sigma);
               }
+              }
             }
           }
           // ---- operands the NEXT layer needs besides the activations
-          if (l == 4) { enc_wait(); write_enc_x(grow[t], nullptr); }
+          if (l == 4) {
+            if (COMP && !vd && it > 0) {      // the encoding overwrites BOTH tiles' stage (enc buffer): both must be consumed
+              mbar_wait(bar(B_STFREE + 0), (uint32_t)((it - 1) & 1), a.watch, 0xC20);
+              mbar_wait(bar(B_STFREE + 1), (uint32_t)((it - 1) & 1), a.watch, 0xC21);
+            }
+            enc_wait(); write_enc_x(grow[t], nullptr);
+          }
           if (l == 6 && it + 1 < niter)       // global loads whose latency must not sit in front of the next encode
             load_point((st + a.nclusters) * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row, pnext[t]);
           if (l == 8) { enc_wait(); write_enc_d(grow[t], SAVE ? gtile[t] + kFDg : nullptr); }
@@ -729,6 +878,10 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             uint8_t* gdst = nullptr;
             if (SAVE) gdst = gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat);
             publish(t, true, gdst, 4);
+            // MODE_FWD_COMP: the stage this tile's final epilogue wrote in the PREVIOUS super-tile is handed to its
+            // compositor warp only now, inside the middle layers, not during the epilogue-bound super-tile boundary
+            // (publish() contains the CTA barrier that orders the 128 writers before this arrive)
+            if (COMP && l == 1 && it > 0 && et == 0) mbar_arrive(bar(B_STFULL + t));
           } else {
             // last layer of this tile.  Without view directions h7 is the last stored layer input: the second panels of
             // both halves go out here (nothing to signal, no MMA follows).
@@ -743,7 +896,11 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               write_first_layer_x(t, pnext[t],
                                   SAVE ? a.acts + (size_t)(stn * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
               signal_ready(t);
-            } else { tc_fence_before(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+            } else {
+              tc_fence_before();
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (COMP && et == 0) mbar_arrive(bar(B_STFULL + t));      // last super-tile: nothing left to hide behind
+            }
           }
         }
       }
@@ -1130,6 +1287,7 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     build_schedule_bwd(true, sched_bwd);
     build_schedule_bwd(false, sched_bwd_novd);
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -1174,6 +1332,10 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD>");
+  } else if (mode == MODE_FWD_COMP) {
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_COMP>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
+    NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
+    return check_launch("nerf_mlp_kernel<FWD_COMP>");
   } else if (mode == MODE_FWD_SAVE) {
     if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64));
     else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE_NV>, a, sched_novd, maps->tm128, maps->tm64));
@@ -1203,6 +1365,28 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
   a.out_ch = use_viewdirs ? 4 : out_ch;
   a.param_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
   return launch_mlp(MODE_FWD, a, use_viewdirs != 0, stream);
+}
+
+extern "C" int nerfb_mlp_fwd_composite_bf16(int R, int S, const float* rays, int ray_width, const float* z, int lindisp,
+                                            int use_viewdirs, int out_ch, const void* packed, float* rec, float* wpart,
+                                            void* stream) {
+  NERFB_REQUIRE(R >= 0 && S > 0 && packed && rays && rec, "nerfb_mlp_fwd_composite_bf16: bad arguments");
+  NERFB_REQUIRE(S % 32 == 0 && S <= 1024, "nerfb_mlp_fwd_composite_bf16: S=%d must be a multiple of 32, at most 1024", S);
+  NERFB_REQUIRE((long long)R * S < 0x7fffffffll, "nerfb_mlp_fwd_composite_bf16: at most 2^31 samples per launch");
+  NERFB_REQUIRE(ray_width >= (use_viewdirs ? 11 : 8), "nerfb_mlp_fwd_composite_bf16: ray_width=%d too small", ray_width);
+  NERFB_REQUIRE(use_viewdirs || (out_ch >= 4 && out_ch <= 5), "nerfb_mlp_fwd_composite_bf16: out_ch=%d unsupported", out_ch);
+  NERFB_REQUIRE(aligned16(packed) && aligned16(rec), "nerfb_mlp_fwd_composite_bf16: packed / rec must be 16-byte aligned");
+  if (R == 0) return NERFB_OK;
+  MlpArgs a{};
+  a.rays = rays; a.rw = ray_width; a.z = z; a.pts = nullptr; a.viewdirs = nullptr;
+  a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = use_viewdirs;
+  a.packed = (const uint8_t*)packed; a.raw = nullptr;
+  a.out_ch = use_viewdirs ? 4 : out_ch;
+  a.param_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
+  a.lindisp = lindisp;
+  a.zstep = S > 1 ? 1.0f / (float)(S - 1) : 0.f;
+  a.comp_rec = rec; a.comp_wpart = wpart;
+  return launch_mlp(MODE_FWD_COMP, a, use_viewdirs != 0, stream);
 }
 
 extern "C" size_t nerfb_train_store_bytes(long long nrows, int which) {

@@ -121,13 +121,6 @@ __global__ void pack_rays_kernel(int n, const float* __restrict__ ro, const floa
   row[6] = near_v; row[7] = far_v;
 }
 
-__device__ __forceinline__ float z_at(int i, int S, float near_v, float far_v, int lindisp) {
-  const float t = linspace01(i, S);
-  const float omt = __fsub_rn(1.0f, t);
-  if (!lindisp) return __fadd_rn(__fmul_rn(near_v, omt), __fmul_rn(far_v, t));
-  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near_v), omt), __fmul_rn(__fdiv_rn(1.0f, far_v), t)));
-}
-
 __global__ void coarse_z_kernel(int R, int S, const float* __restrict__ rays, int rw, int lindisp,
                                 const float* __restrict__ t_rand, float* __restrict__ z) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -314,9 +314,83 @@ composite_resample_kernel(int R, int S, int N, int P, const float* __restrict__ 
                      z_samples ? z_samples + (size_t)r * N : nullptr, nullptr, z_std ? z_std + r : nullptr, s_wts + S, lane);
 }
 
+// The coarse pass of the fused inference path: nerf_mlp_kernel<FWD_COMP> left, per ray, the segment records and the
+// per-sample partial weights w'_i = alpha_i * (exclusive product inside the 32-sample segment).  This kernel (one warp per
+// ray) multiplies in the transmittance in front of each segment (product of the earlier segments' Q, fp64), writes the
+// coarse maps rgb0 / disp0 / acc0 / depth0, and runs the z_mid / sample_pdf / sort / z_std block on the finished weights,
+// which stay in shared memory.  Coarse depths come from `z` or, when NULL, are recomputed from the rays' near / far.
+__global__ void __launch_bounds__(32 * PW)
+resample_records_kernel(int R, int S, int N, int P, const float* __restrict__ rays, int rw, const float* __restrict__ z,
+                        int lindisp, const float* __restrict__ wpart, const float* __restrict__ rec, int white, int det,
+                        const float* __restrict__ u_in, float* __restrict__ rgb, float* __restrict__ disp,
+                        float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ z_out,
+                        float* __restrict__ z_samples, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * PW + wib;
+  if (r >= R) return;
+  float* s_wts = smem + (size_t)wib * (2 * S + 3 * (S - 1) + P);
+  float* s_z = s_wts + S;
+  const int nseg = S >> 5;
+  const float* ray = rays + (size_t)r * rw;
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+  if (lane < nseg) {
+    const float4* q = reinterpret_cast<const float4*>(rec + ((size_t)r * nseg + lane) * 8);
+    ra = __ldg(q);
+    rb = __ldg(q + 1);
+  }
+  double T = 1.0;
+  float asum = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, dsum = 0.f;
+  const float near_v = __ldg(ray + 6), far_v = __ldg(ray + 7);
+  for (int s = 0; s < nseg; ++s) {
+    const float qlo = __shfl_sync(0xffffffffu, ra.x, s), qhi = __shfl_sync(0xffffffffu, ra.y, s);
+    const float A = __shfl_sync(0xffffffffu, ra.z, s), C0 = __shfl_sync(0xffffffffu, ra.w, s);
+    const float C1 = __shfl_sync(0xffffffffu, rb.x, s), C2 = __shfl_sync(0xffffffffu, rb.y, s);
+    const float D = __shfl_sync(0xffffffffu, rb.z, s);
+    const float Tf = (float)T;
+    asum = fmaf(Tf, A, asum); c0 = fmaf(Tf, C0, c0); c1 = fmaf(Tf, C1, c1); c2 = fmaf(Tf, C2, c2); dsum = fmaf(Tf, D, dsum);
+    const int i = 32 * s + lane;
+    s_wts[i] = __fmul_rn(Tf, __ldg(wpart + (size_t)r * S + i));
+    s_z[i] = z ? __ldg(z + (size_t)r * S + i) : z_at(i, S, near_v, far_v, lindisp);
+    T *= (double)qlo;
+  }
+  if (lane == 0) {
+    if (white) {
+      const float bg = __fsub_rn(1.0f, asum);
+      c0 += bg; c1 += bg; c2 += bg;
+    }
+    rgb[3 * r + 0] = c0; rgb[3 * r + 1] = c1; rgb[3 * r + 2] = c2;
+    if (depth) depth[r] = dsum;
+    if (acc) acc[r] = asum;
+    if (disp) disp[r] = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(dsum, fmaxf(1e-10f, asum)), 1e-10f));
+  }
+  __syncwarp();
+  hierarchical_z_ray(S, N, P, s_z, s_wts, det, u_in ? u_in + (size_t)r * N : nullptr, z_out + (size_t)r * (S + N),
+                     z_samples ? z_samples + (size_t)r * N : nullptr, nullptr, z_std ? z_std + r : nullptr, s_z + S, lane);
+}
+
 }  // namespace nerfb
 
 using namespace nerfb;
+
+extern "C" int nerfb_resample_records(int R, int S, int N, const float* rays, int ray_width, const float* z, int lindisp,
+                                      const float* wpart, const float* rec, int white_bkgd, int det, const float* u,
+                                      float* rgb, float* disp, float* acc, float* depth, float* z_out, float* z_samples,
+                                      float* z_std, void* stream) {
+  NERFB_REQUIRE(R >= 0 && S >= 32 && S % 32 == 0 && S <= 1024 && N >= 1 && rays && ray_width >= 8 && wpart && rec && rgb && z_out,
+                "nerfb_resample_records: bad arguments (R=%d S=%d N=%d)", R, S, N);
+  NERFB_REQUIRE(det || u, "nerfb_resample_records: det=0 needs u");
+  NERFB_REQUIRE(aligned16(rec), "nerfb_resample_records: rec must be 16-byte aligned");
+  int P = 1;
+  while (P < S + N) P <<= 1;
+  const size_t smem = (size_t)PW * (2 * S + 3 * (S - 1) + P) * sizeof(float);
+  NERFB_REQUIRE(smem <= 48 * 1024, "nerfb_resample_records: S+N too large (%d+%d)", S, N);
+  if (R == 0) return NERFB_OK;
+  resample_records_kernel<<<cdiv(R, PW), 32 * PW, smem, as_stream(stream)>>>(R, S, N, P, rays, ray_width, z, lindisp, wpart,
+                                                                            rec, white_bkgd, det, u, rgb, disp, acc, depth,
+                                                                            z_out, z_samples, z_std);
+  return check_launch("resample_records_kernel");
+}
 
 extern "C" int nerfb_sample_pdf(int R, int M, int N, const float* bins, int ld_bins, const float* weights,
                                 int ld_w, int det, const float* u, float* samples, long long* inds,

@@ -293,6 +293,55 @@ def _mlp_fwd_bf16(R, S, rays, z, pts, viewdirs, use_viewdirs, out_ch, packed, ra
     return raw
 
 
+# ---------------------------- inference: network pass + compositing in one launch (raw never materialised)
+
+def mlp_fwd_composite_bf16(R, S, rays, z, lindisp, use_viewdirs, out_ch, packed, want_wpart: bool):
+    """nerf_mlp_kernel<FWD_COMP> -> (rec [R,S/32,8], wpart [R,S] | None): the network pass with the compositing of every
+    32-sample segment done in-kernel; finish with composite_finish (final pass) or resample_records (coarse pass)."""
+    L.require_cuda(rays, z, packed)
+    dev = rays.device
+    rec = torch.empty((R, S // 32, 8), dtype=torch.float32, device=dev)
+    wpart = torch.empty((R, S), dtype=torch.float32, device=dev) if want_wpart else None
+    call = lambda: L.check(L.load().nerfb_mlp_fwd_composite_bf16(
+        int(R), int(S), L.ptr(rays), rays.shape[1], L.ptr(z), int(bool(lindisp)), int(bool(use_viewdirs)), int(out_ch),
+        L.ptr(packed), L.ptr(rec), L.ptr(wpart), L.stream()), "nerfb_mlp_fwd_composite_bf16")
+    if _mlp_events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record()
+        _mlp_events.append((e0, e1, int(R) * int(S), bool(use_viewdirs)))
+    else:
+        call()
+    _count()
+    return rec, wpart
+
+
+def composite_finish(rec, white_bkgd):
+    """(rgb [R,3], disp, acc, depth) from the segment records of mlp_fwd_composite_bf16."""
+    R, nseg = rec.shape[0], rec.shape[1]
+    rgb, disp, acc, depth = _empty((R, 3), rec), _empty((R,), rec), _empty((R,), rec), _empty((R,), rec)
+    L.check(L.load().nerfb_composite_finish(int(R), int(nseg), L.ptr(rec), int(bool(white_bkgd)), L.ptr(rgb), L.ptr(disp),
+                                            L.ptr(acc), L.ptr(depth), L.stream()), "nerfb_composite_finish")
+    _count()
+    return rgb, disp, acc, depth
+
+
+def resample_records(R, S, N, rays, z, lindisp, wpart, rec, white_bkgd, det=True, u=None, want_samples=False):
+    """Finish the fused coarse pass: (rgb0, disp0, acc0, depth0, z_out [R,S+N], z_samples|None, z_std)."""
+    L.require_cuda(rays, z, wpart, rec, u)
+    rgb, disp, acc, depth = _empty((R, 3), rays), _empty((R,), rays), _empty((R,), rays), _empty((R,), rays)
+    z_out, z_std = _empty((R, S + N), rays), _empty((R,), rays)
+    z_samples = _empty((R, N), rays) if want_samples else None
+    if u is not None:
+        u = L.f32c(u)
+    L.check(L.load().nerfb_resample_records(int(R), int(S), int(N), L.ptr(rays), rays.shape[1], L.ptr(z),
+                                            int(bool(lindisp)), L.ptr(wpart), L.ptr(rec), int(bool(white_bkgd)),
+                                            int(bool(det)), L.ptr(u), L.ptr(rgb), L.ptr(disp), L.ptr(acc), L.ptr(depth),
+                                            L.ptr(z_out), L.ptr(z_samples), L.ptr(z_std), L.stream()),
+            "nerfb_resample_records")
+    _count()
+    return rgb, disp, acc, depth, z_out, z_samples, z_std
+
+
 # ------------------------------------------ tensor-core MLP backward (bf16)
 
 def train_store_bytes(nrows: int, which: int) -> int:

@@ -228,6 +228,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     if network_fine is not None:
         params += list(network_fine.parameters())
     cfg["train"] = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if not cfg["train"] and not retraw and noise_c is None and noise_f is None and _composite_in_kernel(cfg):
+        return _render_rays_inference(ray_batch, cfg, t_rand, u)
     (rgb, disp, acc, depth, weights, raw, z_vals, rgb0, disp0, acc0, depth0, z_std, z_samples) = \
         AG.RenderRaysFn.apply(cfg, ray_batch, t_rand, u, noise_c, noise_f, *params)
     ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
@@ -242,6 +244,43 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
                 print(f"! [Numerical Error] {k} contains nan or inf.")
     return ret
+
+
+def _composite_in_kernel(cfg) -> bool:
+    """Inference in bf16 mode with the canonical networks and whole 32-sample segments per ray: the compositing runs
+    inside the fused MLP kernel (nerf_mlp_kernel<FWD_COMP>) and the per-sample raw outputs never reach HBM."""
+    S, N = cfg["N_samples"], cfg["N_importance"]
+    nets = [cfg["network_fn"]] + ([cfg["network_fine"]] if cfg["network_fine"] is not None else [])
+    if mlp.get_precision() != "bf16" or not all(n.is_canonical() and (n.use_viewdirs or n.output_ch in (4, 5)) for n in nets):
+        return False
+    if S % 32 != 0 or S > 1024 or (N > 0 and ((S + N) % 32 != 0 or S + N > 1024 or S < 3)):
+        return False
+    return os.environ.get("NERFB200_COMPOSITE_IN_KERNEL", "1") != "0"
+
+
+def _render_rays_inference(rays, cfg, t_rand, u):
+    """render_rays (ipynb:359-492) for inference: coarse network pass with the compositing of every 32-sample segment
+    inside the kernel -> coarse maps + hierarchical resampling from the segment records (coarse weights rebuilt on-chip)
+    -> fine network pass + compositing -> finish of the rays from the records (1 byte per sample).  Coarse depths are
+    computed inside the kernels (written to HBM only when perturb > 0 supplies jitter); raw is never written."""
+    net_c, net_f = cfg["network_fn"], cfg["network_fine"]
+    R, S, N = rays.shape[0], cfg["N_samples"], cfg["N_importance"]
+    white, lindisp = cfg["white_bkgd"], cfg["lindisp"]
+    z_c = ops.coarse_z(rays, S, lindisp, t_rand) if t_rand is not None else None
+    vd = bool(net_c.use_viewdirs)
+    rec, wpart = ops.mlp_fwd_composite_bf16(R, S, rays, z_c, lindisp, vd, net_c.output_ch, mlp.packed_weights(net_c),
+                                            want_wpart=N > 0)
+    if N == 0:
+        rgb, disp, acc, depth = ops.composite_finish(rec, white)
+        return {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth}
+    det = (t_rand is None and u is None)
+    rgb0, disp0, acc0, depth0, z_f, _, z_std = ops.resample_records(R, S, N, rays, z_c, lindisp, wpart, rec, white, det, u)
+    run = net_f if net_f is not None else net_c
+    rec_f, _ = ops.mlp_fwd_composite_bf16(R, S + N, rays, z_f, False, bool(run.use_viewdirs), run.output_ch,
+                                          mlp.packed_weights(run), want_wpart=False)
+    rgb, disp, acc, depth = ops.composite_finish(rec_f, white)
+    return {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "rgb0": rgb0, "disp0": disp0, "acc0": acc0, "z_std": z_std,
+            "depth0": depth0, "depth_map": depth}
 
 
 def _render_rays_generic(ray_batch, network_fn, network_query_fn, N_samples, retraw, lindisp, perturb,
