@@ -265,6 +265,12 @@ int nerfb_umma_selftest(int cta_group, int N, int K, const float* A, const float
 /* Same for MN-major operands (the wgrad form): C[128,N] = At^T Bt, At [K,128], Bt [K,N] row-major,
  * K multiple of 16 (<= 128), N multiple of 64 (<= 256), single CTA. */
 int nerfb_umma_selftest_mn(int N, int K, const float* At, const float* Bt, float* C, void* stream);
+/* bias-by-MMA form of the fused MLP (2-CTA pair): C [256,N] = A' Bb^T + A Bw^T, A [256,64], Bw [N,64] as
+ * 128B-swizzled K-major chunks, Bb [N,16] as a no-swizzle K-major tile read by ONE K=16 MMA whose A operand A' is either
+ * A[:, 48:64] (A8 NULL) or the [8,16] tile A8 repeated for every 8 rows (stride between 8-row groups = 0: a 256-byte
+ * constant operand); N = 128 or 256. */
+int nerfb_umma_selftest_bias(int N, const float* A, const float* Bw, const float* Bb, const float* A8, float* C,
+                             void* stream);
 /* Test hook (host only, no GPU): static schedule of the fused MLP kernel, which = 0 forward with view directions,
  * 1 forward without, 2 data-gradient chain, 3 data-gradient chain without view directions.  h_loads: 2 ints per load {blob offset, bytes per CTA}; h_ops: 5 ints per
  * op {load, tile, A source chunk (4 = encoding buffer), flags (1 first, 2 last, 4 release slot, 8 release enc,

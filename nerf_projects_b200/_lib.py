@@ -59,6 +59,7 @@ _SIGS = {
     "nerfb_mlp_wgrad_nv_bf16": ([_ll, _i, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp], _i),
     "nerfb_umma_selftest": ([_i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "nerfb_umma_selftest_mn": ([_i, _i, _vp, _vp, _vp, _vp], _i),
+    "nerfb_umma_selftest_bias": ([_i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_bulk_probe": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "nerfb_contention_probe": ([_vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "nerfb_debug_schedule": ([_i] + [C.POINTER(_i)] * 6, _i),

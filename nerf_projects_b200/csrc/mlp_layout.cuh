@@ -23,6 +23,17 @@ constexpr int kNumFullChunks = 34;             // L0(1) L1-4(16) L5(1+4) L6-7(8)
 constexpr int kNumViewChunks = 5;              // gamma(d) part + 4 feature parts
 constexpr int kChunkAreaVD = kNumFullChunks * kChunkFull + kNumViewChunks * kChunkViews;
 constexpr int kChunkAreaNoVD = 30 * kChunkFull;
+// Bias tiles (forward): a layer's bias is added ON THE TENSOR CORES by one extra K = 16 MMA at the start of each tile's
+// block: A operand = a constant 256-byte tile ([8 rows x 16] bf16, columns 0 and 1 = 1.0, read by every 8-row group through
+// a descriptor whose row-group stride is 0), B operand = the layer's [N x 16] bf16 tile with column 0 = bf16(bias) and
+// column 1 = bf16(bias - column 0) (a 16-bit mantissa: the rounding of a bias is systematic over all samples, so a single
+// bf16 is not enough -- measured on the calibrated scenes); no-swizzle K-major (tc05::nosw16_offset), two CTA halves of
+// 4 KB.  Tiles in blob order: pts_linears 0..7[, feature, views].
+constexpr int kBiasTileHalf = 4096;
+constexpr int kBiasTileBytes = 2 * kBiasTileHalf;
+constexpr int kNumBiasTilesVD = 10, kNumBiasTilesNoVD = 8;
+constexpr int kBiasAreaVD = kNumBiasTilesVD * kBiasTileBytes, kBiasAreaNoVD = kNumBiasTilesNoVD * kBiasTileBytes;
+constexpr int kParamOffVD = kChunkAreaVD + kBiasAreaVD, kParamOffNoVD = kChunkAreaNoVD + kBiasAreaNoVD;
 
 // fp32 parameter block (floats)
 constexpr int kOffBias = 0;                    // 8 x 256 pts biases
@@ -39,7 +50,10 @@ constexpr int kParamBytes = kParamFloats * 4;  // 16432
 constexpr int kSmAct = 0;                      // 2 tiles x 4 chunks
 constexpr int kSmEnc = 2 * 4 * kChunkBytes;    // 131072: gamma(x) / gamma(d) operand chunk
 constexpr int kSmRing = kSmEnc + kChunkBytes;  // 147456
-constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992
+constexpr int kSmParams = kSmRing + kNS * kChunkBytes;  // 212992: fp32 parameter block; its first 8 KB (the pts biases,
+                                                        // not needed in shared memory any more) = two bias-tile buffers
+constexpr int kSmBiasBuf = kSmParams;
+constexpr int kSmOnes = kSmParams + 2 * 4096;           // the constant A operand of the bias MMAs (256 B; feature / views bias floats)
 constexpr int kSmSig = kSmParams + kParamBytes;         // 229424: [2 tiles][2 halves][128] fp32
 constexpr int kSmBars = kSmSig + 2 * 2 * 128 * 4;       // 231472
 constexpr int kNumBars = 2 * kNS + 2 + 2 + 1 + 4;       // w_full, w_empty, act_ready[2], mma_done[2], enc_free, stage_full[2], stage_free[2]

@@ -46,8 +46,11 @@ tc05::Watch get_watch();  // umma_selftest.cu
 // ------------------------------------------------------------- schedule
 // A static program shared by the three asynchronous roles.  Generated on the
 // host (build_schedule) and passed by value.
-struct LoadEnt { uint32_t off; uint32_t bytes; };          // blob offset of the chunk, bytes per CTA
-enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16 };
+// bytes: bytes per CTA of the chunk (8192 or 16384), plus -- when the load also brings the layer's bias tile -- bit 0 set,
+// bit 1 = bias buffer (0/1) and bits 2..5 = index of the tile in the blob's bias area
+struct LoadEnt { uint32_t off; uint32_t bytes; };          // blob offset of the chunk, bytes per CTA (+ bias tile bits)
+enum : uint8_t { F_FIRST = 1, F_LAST = 2, F_REL_SLOT = 4, F_REL_ENC = 8, F_N128 = 16,
+                 F_BIAS0 = 32, F_BIAS1 = 64 };   // block starts with the layer's bias MMA, tile in bias buffer 0 / 1
 // One op = 4 MMAs (K = 64) of one tile over one weight chunk.  Consecutive ops of the same tile and layer form a
 // BLOCK (one pass of the tile over the layer): `tile` carries the block length in its high nibble on the block's
 // first op; the MMA issuer handles a block as one unit with minimal work between its chunks.
@@ -74,38 +77,52 @@ static void build_schedule(bool vd, Sched& s) {
   };
   int blk_first[48], blk_count[48], nblk = 0;
   auto block = [&](int first, int count) { blk_first[nblk] = first; blk_count[nblk++] = count; };
+  int nbias = 0;
+  // Every layer's bias tile (mlp_layout.cuh) arrives with the layer's FIRST load (same barrier) into bias buffer
+  // nbias % 2, and each tile's block starts with the bias MMA.  (Reuse of a buffer two layers later is safe: that load is
+  // issued after the loader waited for a ring slot released by an op of the layer in between, i.e. after every MMA of
+  // this layer; tests/test_schedule_cpu.py checks the distances.)
+  auto bias_on = [&](uint8_t first_load) -> int {
+    const int buf = nbias & 1;
+    s.loads[first_load].bytes |= 1u | ((uint32_t)buf << 1) | ((uint32_t)nbias << 2);
+    ++nbias;
+    return buf ? F_BIAS1 : F_BIAS0;
+  };
   // plain K=256 layer: chunks id0..id0+3, both tiles pass over the resident layer
   auto plain = [&](int id0, bool n128) {
     uint8_t l[4];
     for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
-    const int f = n128 ? F_N128 : 0;
+    const int fb = bias_on(l[0]);
+    const int f = (n128 ? F_N128 : 0);
     block(s.nops, 4);
-    for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
+    for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 0 ? (F_FIRST | fb) : 0) | (k == 3 ? F_LAST : 0));
     block(s.nops, 4);
-    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0) | (k == 3 ? F_LAST : 0));
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? (F_FIRST | fb) : 0) | (k == 3 ? F_LAST : 0));
   };
   // layer with an extra K=64 chunk read from the enc buffer (skip concat / view concat):
   // tile A consumes it first, tile B last, so the 4-slot ring never needs 5 live chunks.
   auto with_enc = [&](int id_enc, int id0, bool n128) {
     const int f = n128 ? F_N128 : 0;
     const uint8_t g = add_load(id_enc, n128);
+    const int fb = bias_on(g);
     uint8_t l[4];
     for (int k = 0; k < 4; ++k) l[k] = add_load(id0 + k, n128);
     const uint8_t g2 = add_load(id_enc, n128);
     block(s.nops, 5);
-    add_op(g, 0, 4, f | F_FIRST | F_REL_SLOT | F_REL_ENC);
+    add_op(g, 0, 4, f | F_FIRST | fb | F_REL_SLOT | F_REL_ENC);
     for (int k = 0; k < 4; ++k) add_op(l[k], 0, k, f | (k == 3 ? F_LAST : 0));
     block(s.nops, 5);
-    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? F_FIRST : 0));
+    for (int k = 0; k < 4; ++k) add_op(l[k], 1, k, f | F_REL_SLOT | (k == 0 ? (F_FIRST | fb) : 0));
     add_op(g2, 1, 4, f | F_LAST | F_REL_SLOT | F_REL_ENC);
   };
   {  // layer 0: K = 64 (gamma(x), written by the epilogue warps into chunk 0 of the tile's own activation buffer),
      // one weight chunk used by both tiles
     const uint8_t g0 = add_load(0, false);
+    const int fb = bias_on(g0);
     block(s.nops, 1);
-    add_op(g0, 0, 0, F_FIRST | F_LAST);
+    add_op(g0, 0, 0, F_FIRST | F_LAST | fb);
     block(s.nops, 1);
-    add_op(g0, 1, 0, F_FIRST | F_LAST | F_REL_SLOT);
+    add_op(g0, 1, 0, F_FIRST | F_LAST | F_REL_SLOT | fb);
   }
   for (int l = 1; l <= 4; ++l) plain(1 + 4 * (l - 1), false);
   with_enc(17, 18, false);          // layer 5: [gamma(x) | h4]
@@ -164,6 +181,7 @@ struct MlpArgs {
   const float* d_raw; // MODE_BWD: [nrows,4]
   const float* d_raw4; // MODE_BWD without view directions: gradient of output channel 4 [nrows] or null
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
+  int bias_off;       // byte offset of the bias-tile area inside `packed` (forward modes)
   // MODE_FWD_COMP: compositing folded into the forward
   int lindisp;        // z == nullptr: coarse depths computed in-kernel from the rays' near / far (z_at)
   float zstep;        // fl(1 / (S - 1)): torch.linspace's step for those depths
@@ -246,7 +264,8 @@ __device__ __forceinline__ void rgb_head_half(const uint32_t (&v)[32], int b, fl
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int c = 64 * HH + 32 * b + j;          // b is a compile-time constant at every call site (unrolled)
-    const float pre = __uint_as_float(v[j]) + c_par[kOffBiasViews + c];
+    const float pre = __uint_as_float(v[j]);      // bias already in the accumulator (bias MMA)
+    (void)c;
     if (SAVE) m = __funnelshift_l(__float_as_uint(pre), m, 1);
     const float x = fmaxf(pre, 0.f);
     xs[j] = x;
@@ -352,7 +371,8 @@ __device__ __noinline__ void composite_tile(const MlpArgs& a, const float4* __re
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc,
-                const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64) {
+                const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
+                const __grid_constant__ CUtensorMap tm32) {
   constexpr bool SAVE = (MODE == MODE_FWD_SAVE || MODE == MODE_FWD_SAVE_NV);
   constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_BWD_NV);
   constexpr bool NV = (MODE == MODE_FWD_SAVE_NV || MODE == MODE_BWD_NV);   // training kernels of the no-view-directions network
@@ -408,8 +428,14 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         (uint32_t)e.load | ((uint32_t)e.tile << 8) | ((uint32_t)e.asrc << 16) | ((uint32_t)e.flags << 24);
   }
   {
+    // (the first 9.5 KB of the block's shared-memory image -- the biases, now added by MMAs -- hold the two bias-tile
+    //  buffers and the constant A operand of the bias MMAs instead)
     const float* gpar = reinterpret_cast<const float*>(a.packed + a.param_off);
-    for (int i = tid; i < kParamFloats; i += kThreads) s_par[i] = __ldg(gpar + i);
+    for (int i = kOffHeadW + tid; i < kParamFloats; i += kThreads) s_par[i] = __ldg(gpar + i);
+  }
+  if (tid < 16) {     // ones tile: [8 rows x 16] bf16, columns 0 and 1 = 1.0 (K group 0 = bytes 0..127, K group 1 = 128..255)
+    *reinterpret_cast<uint4*>(smem + kSmOnes + 16 * tid) = make_uint4(tid < 8 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if (warp == 2) {
     tmem_alloc<2>(sbase + kSmTmemSlot, 512);
@@ -434,12 +460,18 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           if (gl >= kNS) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((gl / kNS) + 1) & 1), a.watch, 0x100 + q);
           tr(0, 0x100 + q);
           const uint2 le2 = reinterpret_cast<const uint2*>(smem + kSmLoads)[q];
-          const LoadEnt le{le2.x, le2.y};
-          if (rank == 0) mbar_arrive_expect_tx(bar(B_FULL + slot), 2 * le.bytes);
+          const LoadEnt le{le2.x, le2.y & ~63u};
+          const bool with_bias = (le2.y & 1u) != 0;
+          if (rank == 0) mbar_arrive_expect_tx(bar(B_FULL + slot), 2 * le.bytes + (with_bias ? 2 * kBiasTileHalf : 0));
           // my half of the chunk = rows [row0, row0 + bytes/128) of the blob viewed as [rows][128 B]
           const int row0 = (int)((le.off + rank * le.bytes) >> 7);
           tma_load_2d_cg2(sbase + kSmRing + slot * kChunkBytes, le.bytes == (uint32_t)kChunkBytes ? &tm128 : &tm64,
                           full_leader + 8 * slot, 0, row0);
+          if (with_bias) {      // the layer's bias tile: my 4 KB half, same barrier as the chunk
+            const uint32_t buf = (le2.y >> 1) & 1u, id = (le2.y >> 2) & 15u;
+            tma_load_2d_cg2(sbase + kSmBiasBuf + buf * kBiasTileHalf, &tm32, full_leader + 8 * slot, 0,
+                            (int)(((uint32_t)a.bias_off + id * kBiasTileBytes + rank * kBiasTileHalf) >> 7));
+          }
           tr(0, 0xA00 + q);
         }
       }
@@ -491,6 +523,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       if (tmem_base != 0) watchdog_fire(a.watch, 0xA12, tmem_base, 0);
       const uint32_t idesc256 = make_idesc_bf16(256, 256), idesc128 = make_idesc_bf16(256, 128);
       const uint64_t desc_hi = make_sdesc_sw128(0);            // everything but the start address
+      const uint64_t d_ones = make_sdesc_nosw(sbase + kSmOnes, 128, 0);    // every 8-row group reads the same 8 rows
+      const uint64_t d_bias0 = make_sdesc_nosw(sbase + kSmBiasBuf, 128, 256);
+      const uint64_t d_bias1 = make_sdesc_nosw(sbase + kSmBiasBuf + kBiasTileHalf, 128, 256);
       const uint32_t* s_ops = reinterpret_cast<const uint32_t*>(smem + kSmOps);
       const int nops = sc.nops, nloads = sc.nloads;
       uint32_t act_cnt0 = 0, act_cnt1 = 0;
@@ -526,7 +561,9 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
             const uint64_t da = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
             const uint64_t db = desc_hi | (uint64_t)(((sbase + kSmRing + slot * kChunkBytes) >> 4) & 0x3FFF);
             const uint32_t idesc = (flags & F_N128) ? idesc128 : idesc256;
-            umma_bf16<2>(d_tmem, da, db, idesc, (flags & F_FIRST) ? 0u : 1u);
+            const bool bias_mma = (flags & (F_BIAS0 | F_BIAS1)) != 0;
+            if (bias_mma) umma_bf16<2>(d_tmem, d_ones, (flags & F_BIAS1) ? d_bias1 : d_bias0, idesc, 0u);
+            umma_bf16<2>(d_tmem, da, db, idesc, ((flags & F_FIRST) && !bias_mma) ? 0u : 1u);
             umma_bf16<2>(d_tmem, da + 2, db + 2, idesc, 1u);
             umma_bf16<2>(d_tmem, da + 4, db + 4, idesc, 1u);
             umma_bf16<2>(d_tmem, da + 6, db + 6, idesc, 1u);
@@ -676,7 +713,6 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           const uint32_t taddr = tmem_base + lane_addr + t * 256;
           if (l <= 8 && !(l == 7 && !vd && !(SAVE && NV))) {
             // ---- hidden layer: bias (+ReLU) -> bf16 -> next A operand; layer 7 also feeds the density head
-            const float* bias = s_par + (l < 8 ? kOffBias + 256 * l : kOffBiasFeat) + 128 * hh;
             const float* hw = s_par + kOffHeadW + 128 * hh;
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
             float sig = 0.f;
@@ -698,15 +734,10 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               if (b < 3) tmem_ld32(taddr + 128 * hh + 32 * (b + 1), v[(b + 1) & 1]);
 #endif
               const uint32_t (&vv)[32] = v[b & 1];
+              // (the layer's bias is already in the accumulator: bias MMA / column 63 of the encoding chunk)
               float x[32];
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 bb = *reinterpret_cast<const float4*>(bias + 32 * b + 4 * j4);
-                x[4 * j4 + 0] = __uint_as_float(vv[4 * j4 + 0]) + bb.x;
-                x[4 * j4 + 1] = __uint_as_float(vv[4 * j4 + 1]) + bb.y;
-                x[4 * j4 + 2] = __uint_as_float(vv[4 * j4 + 2]) + bb.z;
-                x[4 * j4 + 3] = __uint_as_float(vv[4 * j4 + 3]) + bb.w;
-              }
+              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vv[j]);
               if (SAVE && l < 8) {
                 // one funnel shift per unit (column j ends at bit 31 - j), as four independent 8-bit chains so the
                 // shifts do not serialise on one register
@@ -768,7 +799,6 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
           } else if (l == 7) {
             // ---- no view directions: output_linear (out_ch x 256) in fp32 from layer-7 accumulators
             float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            const float* bias = s_par + kOffBias + 256 * 7 + 128 * hh;
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
               uint32_t v[32];
@@ -776,7 +806,7 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float x = fmaxf(__uint_as_float(v[j]) + bias[32 * b + j], 0.f);
+                const float x = fmaxf(__uint_as_float(v[j]), 0.f);      // bias: in the accumulator (bias MMA)
 #pragma unroll
                 for (int k = 0; k < 5; ++k) part[k] = fmaf(x, s_par[kOffHeadW + 256 * k + 128 * hh + 32 * b + j], part[k]);
               }
@@ -1087,6 +1117,10 @@ struct PackChunk {
 struct PackArgs {
   PackChunk ch[kNumFullChunks + kNumViewChunks];
   int nchunks;
+  const float* bias_tile[kNumBiasTilesVD];   // the layers' biases in blob order
+  int bias_rows[kNumBiasTilesVD];            // 256, or 128 for the views layer
+  int nbias;
+  uint32_t bias_area;
   const float* src[8];  // fp32 block sources, see pack kernel
   int out_ch, use_viewdirs;
   const float* bias[10];
@@ -1138,6 +1172,22 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, uint8_t
                            pack_bf16x2(f[6], f[7]));
       *reinterpret_cast<uint4*>(blob + pc.off + (size_t)half * half_rows * 128 + sw128_offset(r, u)) = v;
     }
+  } else if (c < pa.nchunks + pa.nbias) {
+    // bias tile of a layer: [N x 16] bf16, column 0 = bf16(bias), column 1 = bf16(bias - column 0), rest zero; two CTA
+    // halves of N/2 rows in 4 KB each (rows beyond N/2 zero), no-swizzle K-major layout (tc05::nosw16_offset)
+    const int tix = c - pa.nchunks;
+    const int half_rows = pa.bias_rows[tix] / 2;
+    uint8_t* dst = blob + pa.bias_area + (size_t)tix * kBiasTileBytes;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * 128 * 16; idx += gridDim.x * blockDim.x) {
+      const int half = idx >> 11, r = (idx >> 4) & 127, k = idx & 15;
+      float v = 0.f;
+      if (r < half_rows && k < 2) {
+        const float b = __ldg(pa.bias_tile[tix] + half * half_rows + r);
+        const float hi = __bfloat162float(__float2bfloat16(b));
+        v = (k == 0) ? hi : (b - hi);
+      }
+      *reinterpret_cast<__nv_bfloat16*>(dst + (size_t)half * kBiasTileHalf + nosw16_offset(r, k)) = __float2bfloat16(v);
+    }
   } else if (blockIdx.x == 0) {
     fill_param_block(pa, reinterpret_cast<float*>(blob + chunk_area));
   }
@@ -1179,7 +1229,7 @@ extern "C" int nerfb_set_trace(long long* dev_buf) {
 }
 
 extern "C" size_t nerfb_packed_weights_bytes(int use_viewdirs) {
-  return (size_t)(use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD) + kParamBytes;
+  return (size_t)(use_viewdirs ? kParamOffVD : kParamOffNoVD) + kParamBytes;
 }
 
 extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs, int out_ch, void* packed,
@@ -1196,6 +1246,7 @@ extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs
     pa.ch[n++] = PackChunk{w, ld, col0, ncols, nrows, off};
   };
   auto W = [&](int layer) { return h_params[2 * layer]; };
+  for (int l = 0; l < 8; ++l) { pa.bias_tile[pa.nbias] = h_params[2 * l + 1]; pa.bias_rows[pa.nbias++] = 256; }   // bias tiles
   add(W(0), 63, 0, 63, 256);                                         // chunk 0
   for (int l = 1; l <= 4; ++l)
     for (int k = 0; k < 4; ++k) add(W(l), 256, 64 * k, 64, 256);     // 1..16
@@ -1212,6 +1263,8 @@ extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs
                   "nerfb_pack_weights: view-dependent head parameters missing");
     for (int k = 0; k < 4; ++k) add(fw, 256, 64 * k, 64, 256);       // 30..33 feature_linear
     add(vw, 283, 256, 27, 128);                                      // 34: gamma(d) part [feature | gamma(d)]
+    pa.bias_tile[pa.nbias] = h_params[NERFB_P_FEATURE_B]; pa.bias_rows[pa.nbias++] = 256;
+    pa.bias_tile[pa.nbias] = h_params[NERFB_P_VIEWS_B]; pa.bias_rows[pa.nbias++] = 128;
     for (int k = 0; k < 4; ++k) add(vw, 283, 64 * k, 64, 128);       // 35..38
     pa.bias[8] = h_params[NERFB_P_FEATURE_B];
     pa.bias[9] = h_params[NERFB_P_VIEWS_B];
@@ -1226,15 +1279,16 @@ extern "C" int nerfb_pack_weights(const float* const* h_params, int use_viewdirs
     pa.src[1] = h_params[NERFB_P_OUTPUT_B];
   }
   pa.nchunks = n;
-  dim3 grid(2, n + 1);
+  pa.bias_area = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
+  dim3 grid(2, n + pa.nbias + 1);
   pack_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(pa, (uint8_t*)packed,
-                                                          use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD);
+                                                          use_viewdirs ? kParamOffVD : kParamOffNoVD);
   return check_launch("pack_weights_kernel");
 }
 
 // Tensor maps over a packed weight blob viewed as [rows][128 B] uint8 (images are pre-swizzled, so SWIZZLE_NONE):
 // box = 128 rows (one 16 KB chunk half) or 64 rows (views layer).  Cached per blob address.
-struct BlobMaps { const void* ptr; size_t bytes; CUtensorMap tm128, tm64; };
+struct BlobMaps { const void* ptr; size_t bytes; CUtensorMap tm128, tm64, tm32; };
 static int get_blob_maps(const void* blob, size_t bytes, BlobMaps* out) {   // returns a COPY (the cache may evict)
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1258,9 +1312,9 @@ static int get_blob_maps(const void* blob, size_t bytes, BlobMaps* out) {   // r
   const cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
   const cuuint64_t strides[1] = {128};
   const cuuint32_t estr[2] = {1, 1};
-  for (int k = 0; k < 2; ++k) {
-    const cuuint32_t box[2] = {128, k == 0 ? 128u : 64u};
-    const CUresult r = encode(k == 0 ? &m.tm128 : &m.tm64, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), dims,
+  for (int k = 0; k < 3; ++k) {
+    const cuuint32_t box[2] = {128, k == 0 ? 128u : (k == 1 ? 64u : 32u)};      // 32 rows = one 4 KB bias-tile half
+    const CUresult r = encode(k == 0 ? &m.tm128 : (k == 1 ? &m.tm64 : &m.tm32), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), dims,
                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NERFB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for blob %p, %zu bytes", (int)r, blob, bytes);
@@ -1329,21 +1383,21 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
   const size_t blob_bytes = (size_t)a.param_off + kParamBytes;
   if (int rc = get_blob_maps(a.packed, blob_bytes, &maps_v)) return rc;
   if (mode == MODE_FWD) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64, maps->tm32));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD>");
   } else if (mode == MODE_FWD_COMP) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_COMP>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64));
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_COMP>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64, maps->tm32));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD_COMP>");
   } else if (mode == MODE_FWD_SAVE) {
-    if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64));
-    else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE_NV>, a, sched_novd, maps->tm128, maps->tm64));
+    if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE>, a, sched_vd, maps->tm128, maps->tm64, maps->tm32));
+    else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE_NV>, a, sched_novd, maps->tm128, maps->tm64, maps->tm32));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD_SAVE>");
   }
-  if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64));
-  else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD_NV>, a, sched_bwd_novd, maps->tm128, maps->tm64));
+  if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64, maps->tm32));
+  else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD_NV>, a, sched_bwd_novd, maps->tm128, maps->tm64, maps->tm32));
   NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
   return check_launch("nerf_mlp_kernel<BWD>");
 }
@@ -1363,7 +1417,8 @@ extern "C" int nerfb_mlp_fwd_bf16(int R, int S, const float* rays, int ray_width
   a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = use_viewdirs;
   a.packed = (const uint8_t*)packed; a.raw = raw;
   a.out_ch = use_viewdirs ? 4 : out_ch;
-  a.param_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
+  a.param_off = use_viewdirs ? kParamOffVD : kParamOffNoVD;
+  a.bias_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
   return launch_mlp(MODE_FWD, a, use_viewdirs != 0, stream);
 }
 
@@ -1382,7 +1437,8 @@ extern "C" int nerfb_mlp_fwd_composite_bf16(int R, int S, const float* rays, int
   a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = use_viewdirs;
   a.packed = (const uint8_t*)packed; a.raw = nullptr;
   a.out_ch = use_viewdirs ? 4 : out_ch;
-  a.param_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
+  a.param_off = use_viewdirs ? kParamOffVD : kParamOffNoVD;
+  a.bias_off = use_viewdirs ? kChunkAreaVD : kChunkAreaNoVD;
   a.lindisp = lindisp;
   a.zstep = S > 1 ? 1.0f / (float)(S - 1) : 0.f;
   a.comp_rec = rec; a.comp_wpart = wpart;
@@ -1407,7 +1463,8 @@ extern "C" int nerfb_mlp_fwd_save_bf16(int R, int S, const float* rays, int ray_
   a.rays = rays; a.rw = ray_width; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
   a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = 1;
   a.packed = (const uint8_t*)packed; a.raw = raw; a.out_ch = 4;
-  a.param_off = kChunkAreaVD;
+  a.param_off = kParamOffVD;
+  a.bias_off = kChunkAreaVD;
   a.acts = (uint8_t*)acts;
   a.masks = (uint8_t*)masks;
   return launch_mlp(MODE_FWD_SAVE, a, true, stream);
@@ -1475,7 +1532,8 @@ extern "C" int nerfb_mlp_fwd_save_nv_bf16(int R, int S, const float* rays, int r
   a.rays = rays; a.rw = ray_width; a.z = z; a.pts = pts; a.viewdirs = nullptr;
   a.S = S; a.nrows = (long long)R * S; a.use_viewdirs = 0;
   a.packed = (const uint8_t*)packed; a.raw = raw; a.out_ch = out_ch;
-  a.param_off = kChunkAreaNoVD;
+  a.param_off = kParamOffNoVD;
+  a.bias_off = kChunkAreaNoVD;
   a.acts = (uint8_t*)acts;
   a.masks = (uint8_t*)masks;
   return launch_mlp(MODE_FWD_SAVE, a, false, stream);
@@ -1528,7 +1586,7 @@ extern "C" int nerfb_debug_schedule(int which, int* h_nloads, int* h_nops, int* 
   static Sched s;
   if (which >= 2) build_schedule_bwd(which == 2, s); else build_schedule(which == 0, s);
   *h_nloads = s.nloads; *h_nops = s.nops; *h_nlayers = s.nlayers; *h_ring_slots = kNS;
-  for (int i = 0; i < s.nloads; ++i) { h_loads[2 * i] = (int)s.loads[i].off; h_loads[2 * i + 1] = (int)s.loads[i].bytes; }
+  for (int i = 0; i < s.nloads; ++i) { h_loads[2 * i] = (int)s.loads[i].off; h_loads[2 * i + 1] = (int)(s.loads[i].bytes & ~63u); }
   for (int i = 0; i < s.nops; ++i) {
     h_ops[5 * i + 0] = s.ops[i].load; h_ops[5 * i + 1] = s.ops[i].tile & 0xF; h_ops[5 * i + 2] = s.ops[i].asrc;
     h_ops[5 * i + 3] = s.ops[i].flags; h_ops[5 * i + 4] = s.ops[i].tile >> 4;

@@ -330,6 +330,21 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
   return d;
 }
+// K-major operand WITHOUT swizzle (canonical "interleave" layout): core matrices of 8 rows x 16 bytes (8 bf16 along K)
+// stored as 128 contiguous bytes; LBO = byte distance between the core matrices of consecutive K groups, SBO = byte
+// distance between consecutive 8-row groups.  Used for the [rows x 16] bias tiles of the fused MLP (one K=16 MMA).
+__device__ __forceinline__ uint64_t make_sdesc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+// byte offset of element (row, k) of a [rows x 16] bf16 tile in that layout with LBO = 128, SBO = 256
+__host__ __device__ __forceinline__ uint32_t nosw16_offset(uint32_t row, uint32_t k) {
+  return (row >> 3) * 256u + (k >> 3) * 128u + (row & 7u) * 16u + (k & 7u) * 2u;
+}
 // advance along K inside the 128-byte swizzle atom: +32 B per UMMA_K=16 bf16
 __device__ __forceinline__ uint64_t sdesc_advance_k(uint64_t d, int k16) { return d + (uint64_t)(k16 * 2); }
 

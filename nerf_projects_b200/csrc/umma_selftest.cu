@@ -101,6 +101,68 @@ umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __r
   if (warp == 0) tmem_dealloc<CG>(tmem_base, ncols);
 }
 
+// Bias-by-MMA self-test (the form the fused MLP uses to add a layer's bias on the tensor cores): 2-CTA pair,
+// C[256,N] = A[:, 48:64] Bb^T + A Bw^T with A [256,64] and Bw [N,64] staged as 128B-swizzled K-major chunks and the bias
+// tile Bb [N,16] staged in the NO-swizzle K-major layout (nosw16_offset); the first MMA reads K slice 3 of the A chunk.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_selftest_bias_kernel(int N, const float* __restrict__ A, const float* __restrict__ Bw, const float* __restrict__ Bb,
+                          const float* __restrict__ A8, float* __restrict__ C, Watch watch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int nb_rows = N / 2;
+  uint8_t* sA = smem;                             // 16 KB
+  uint8_t* sB = smem + 16384;                     // nb_rows x 128 B
+  uint8_t* sBias = smem + 16384 + 16384;          // nb_rows x 32 B, no swizzle
+  uint8_t* sA8 = sBias + 8192;                    // A8 != null: [8 rows x 16] bf16, no swizzle, every 8-row group aliases it (SBO = 0)
+  if (A8 != nullptr)
+    for (int idx = tid; idx < 8 * 16; idx += 128)
+      *reinterpret_cast<__nv_bfloat16*>(sA8 + nosw16_offset(idx / 16, idx % 16)) = __float2bfloat16(A8[idx]);
+  stage_operand(sA, A + (size_t)rank * 128 * 64, 128, 64, 64, tid, 128);
+  stage_operand(sB, Bw + (size_t)rank * nb_rows * 64, nb_rows, 64, 64, tid, 128);
+  for (int idx = tid; idx < nb_rows * 16; idx += 128) {
+    const int n = idx / 16, k = idx % 16;
+    *reinterpret_cast<__nv_bfloat16*>(sBias + nosw16_offset(n, k)) = __float2bfloat16(Bb[((size_t)rank * nb_rows + n) * 16 + k]);
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) { mbar_init(smem_u32(&bar_done), 1); fence_barrier_init(); }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) { tmem_alloc<2>(smem_u32(&tmem_base_slot), ncols); tmem_relinquish<2>(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, N);
+    const uint64_t da = make_sdesc_sw128(smem_u32(sA));
+    const uint64_t db = make_sdesc_sw128(smem_u32(sB));
+    const uint64_t dbias = make_sdesc_nosw(smem_u32(sBias), 128, 256);
+    if (A8 != nullptr) umma_bf16<2>(tmem_base, make_sdesc_nosw(smem_u32(sA8), 128, 0), dbias, idesc, 0u);
+    else umma_bf16<2>(tmem_base, sdesc_advance_k(da, 3), dbias, idesc, 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16<2>(tmem_base, sdesc_advance_k(da, k), sdesc_advance_k(db, k), idesc, 1u);
+    umma_commit<2>(smem_u32(&bar_done));
+  }
+  mbar_wait(smem_u32(&bar_done), 0, watch, 3);
+  tc_fence_after();
+  const int row = warp * 32 + (tid & 31);
+  float* crow = C + ((size_t)rank * 128 + row) * N;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) crow[c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc<2>(tmem_base, ncols);
+}
+
 // MN-major self-test (the wgrad operand form): C[128,N] = At^T Bt with At [K,128] and Bt [K,N]
 // row-major, staged as [K rows x 64-col panels] swizzled images, K multiple of 16 (<= 128).
 __global__ void __launch_bounds__(128, 1)
@@ -311,6 +373,16 @@ extern "C" int nerfb_umma_selftest_mn(int N, int K, const float* At, const float
   NERFB_CUDA(cudaFuncSetAttribute(umma_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_mn_kernel<<<1, 128, smem, as_stream(stream)>>>(N, K, At, Bt, C, w);
   return check_launch("umma_selftest_mn_kernel");
+}
+
+extern "C" int nerfb_umma_selftest_bias(int N, const float* A, const float* Bw, const float* Bb, const float* A8, float* C,
+                                        void* stream) {
+  NERFB_REQUIRE((N == 256 || N == 128) && A && Bw && Bb && C, "nerfb_umma_selftest_bias: bad arguments (N=%d)", N);
+  const size_t smem = 16384 + 16384 + 8192 + 256 + 1024;
+  tc05::Watch w = get_watch();
+  NERFB_CUDA(cudaFuncSetAttribute(umma_selftest_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_bias_kernel<<<2, 128, smem, as_stream(stream)>>>(N, A, Bw, Bb, A8, C, w);
+  return check_launch("umma_selftest_bias_kernel");
 }
 
 extern "C" const unsigned long long* nerfb_watchdog_record(void) {

@@ -419,6 +419,16 @@ def umma_selftest(A, B, cta_group=1):
     return Cm
 
 
+def umma_selftest_bias(A, Bw, Bb, A8=None):
+    N = Bw.shape[0]
+    assert A.shape == (256, 64) and Bw.shape == (N, 64) and Bb.shape == (N, 16) and (A8 is None or A8.shape == (8, 16))
+    Cm = _empty((256, N), A)
+    L.check(L.load().nerfb_umma_selftest_bias(N, L.ptr(A), L.ptr(Bw), L.ptr(Bb), L.ptr(A8), L.ptr(Cm), L.stream()),
+            "nerfb_umma_selftest_bias")
+    _count()
+    return Cm
+
+
 def umma_selftest_mn(At, Bt):
     K, N = Bt.shape
     assert At.shape == (K, 128)

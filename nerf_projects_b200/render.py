@@ -329,9 +329,30 @@ def _render_rays_generic(ray_batch, network_fn, network_query_fn, N_samples, ret
     return ret
 
 
+def _chunk_period(kwargs) -> int:
+    """Rays after which the fused bf16 kernel's assignment of samples to tile slots repeats: the smallest r with
+    r * S = 0 (mod 512 rows per super-tile) for both passes.  Cutting chunks at multiples of it makes a ray's result
+    independent of `chunk` bit for bit (the two row tiles of a CTA accumulate the K chunks of the skip / view layers in
+    different orders -- the kernel's only position dependence)."""
+    import math
+    S = int(kwargs.get("N_samples", 0) or 0)
+    N = int(kwargs.get("N_importance", 0) or 0)
+    if S <= 0:
+        return 1
+    p = 512 // math.gcd(S, 512)
+    if N > 0:
+        q = 512 // math.gcd(S + N, 512)
+        p = p * q // math.gcd(p, q)
+    return p
+
+
 def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
-    """ipynb:514-548."""
+    """ipynb:514-548.  `chunk` is a memory cap: it is rounded down to a multiple of the tile-slot period of the fused
+    kernel (8 rays for 64 + 128 samples) so that results do not depend on it, bit for bit."""
     all_ret = {}
+    period = _chunk_period(kwargs)
+    if chunk > period:
+        chunk = chunk // period * period
     for i in range(0, rays_flat.shape[0], chunk):
         with RNG.advanced(i):      # no-op unless a keyed_rng context is active
             ret = render_rays(rays_flat[i:i + chunk], **kwargs)

@@ -35,6 +35,30 @@ def test_umma_selftest(cg, N, K):
     assert err < 1e-3, f"max err {err}"
 
 
+@pytest.mark.parametrize("aliased", [False, True])
+@pytest.mark.parametrize("N", [256, 128])
+def test_umma_selftest_bias_tile(N, aliased):
+    """The bias-by-MMA form of the fused MLP: one K=16 MMA whose B operand is a [N,16] tile in the NO-swizzle K-major
+    layout and whose A operand is K slice 3 of a swizzled chunk, or (aliased) a 256-byte [8,16] tile that every 8-row
+    group of the 256 rows reads (descriptor stride between row groups = 0) -- followed by the accumulating K=64 MMAs."""
+    from nerf_projects_b200 import ops, _lib
+    gen = torch.Generator().manual_seed(N)
+    A = torch.randn(256, 64, generator=gen)
+    Bw = torch.randn(N, 64, generator=gen)
+    Bb = torch.randn(N, 16, generator=gen)
+    A8 = torch.randn(8, 16, generator=gen) if aliased else None
+    try:
+        C = ops.umma_selftest_bias(A.to(DEV), Bw.to(DEV), Bb.to(DEV), A8.to(DEV) if aliased else None)
+        torch.cuda.synchronize()
+    except Exception:
+        print("watchdog:", _lib.watchdog_record())
+        raise
+    A1 = A8.repeat(32, 1) if aliased else A[:, 48:64]
+    ref = bf16r(A).double() @ bf16r(Bw).double().T + bf16r(A1).double() @ bf16r(Bb).double().T
+    err = (C.cpu().double() - ref).abs().max().item()
+    assert err < 1e-3, f"max err {err}"
+
+
 @pytest.mark.parametrize("N,K", [(256, 128), (128, 64), (64, 16), (256, 48)])
 def test_umma_selftest_mn_major(N, K):
     """MN-major operands (contraction over the rows of the stored tiles) -- the wgrad form."""

@@ -7,7 +7,7 @@ import pytest
 
 from nerf_projects_b200 import _lib
 
-F_FIRST, F_LAST, F_REL_SLOT, F_REL_ENC, F_N128 = 1, 2, 4, 8, 16
+F_FIRST, F_LAST, F_REL_SLOT, F_REL_ENC, F_N128, F_BIAS0, F_BIAS1 = 1, 2, 4, 8, 16, 32, 64
 
 
 def schedule(which):
@@ -66,6 +66,32 @@ def test_schedule_invariants(which, nlayers, nloads):
     # chunk sizes: 16 KB per CTA, 8 KB for the N=128 (views) layer
     for o in ops:
         assert loads[o["load"]][1] == (8192 if o["flags"] & F_N128 else 16384)
+    # bias MMAs (forward schedules): EVERY block starts with one -- and only there -- from the bias buffer the layer's tile
+    # was loaded into; buffers alternate from layer to layer (also across the wrap to the next super-tile: an even number
+    # of layers); the tile rides on the layer's first load, and the first load of layer j+2 is more than `ring` loads
+    # after the first load of layer j+1, so it is issued only after every MMA of layer j (see mlp_tc.cu: build_schedule)
+    bias_blocks = [(b, n) for b, n in blocks if ops[b]["flags"] & (F_BIAS0 | F_BIAS1)]
+    if which in (0, 1):
+        assert bias_blocks == blocks and nlayers % 2 == 0
+        bufs = [1 if ops[b]["flags"] & F_BIAS1 else 0 for b, _ in blocks]
+        assert bufs == [(i // 2) % 2 for i in range(len(bufs))]
+        for b, n in blocks:
+            assert not (ops[b]["flags"] & F_BIAS0 and ops[b]["flags"] & F_BIAS1)
+            assert not any(o["flags"] & (F_BIAS0 | F_BIAS1) for o in ops[b + 1:b + n])
+        firsts = [min(o["load"] for o in ops[b:b + n]) for b, n in blocks[::2]]        # first load of every layer
+        assert firsts == sorted(firsts) and firsts[0] == 0
+        # the tile of layer j+2 overwrites the buffer of layer j: the loader issues that load (index q, possibly in the
+        # next super-tile) only after the op that releases load q - ring has completed; that op must not precede the LAST
+        # bias MMA of layer j, which is issued at the start of tile 1's block of layer j (a commit covers every MMA
+        # issued before it, so "the same op" is enough)
+        nl, nb = len(loads), len(firsts)
+        for j in range(nb):
+            q = firsts[(j + 2) % nb] + (nl if j + 2 >= nb else 0)
+            prev = q - ring
+            rel_op = last_use[prev % nl] + (len(ops) if prev >= nl else 0)
+            assert rel_op >= blocks[2 * j + 1][0], f"bias buffer of layer {j} may be overwritten while in use"
+    else:
+        assert not bias_blocks
     # wrap-around: the first loads of the next iteration reuse the slots of the last loads of this one
     for q in range(ring):
         prev = len(loads) - ring + q
