@@ -239,6 +239,14 @@ int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, const void* pa
                              const void* masks, void* gstore, void* stream);
 int nerfb_mlp_wgrad_bf16(long long nrows, const void* acts, const void* gstore,
                          const float* d_raw_padded, float* const* h_grads, void* stream);
+/* nerfb_mlp_bwd_chain_bf16 + nerfb_mlp_wgrad_bf16 in ONE cooperative launch: `chain_sms` SMs (even) run the data-gradient
+ * chain, the others the weight-gradient jobs, which read each 128-sample tile's dY panels as soon as the chain has stored
+ * them -- from L2, not from HBM -- and overlap their tensor work with the chain's.  flags: [ntiles * 20] ints (ntiles =
+ * 4 * ceil(nrows / 512)), zero when allocated; epoch: a value not used with this flags buffer before (1, 2, 3, ...).
+ * Needs at least chain_sms / 2 super-tiles of 512 samples. */
+int nerfb_mlp_bwd_fused_bf16(long long nrows, const float* d_raw_padded, const void* packed_bwd, const void* masks,
+                             const void* acts, void* gstore, float* const* h_grads, int* flags, int epoch, int chain_sms,
+                             void* stream);
 /* The same three steps for the network WITHOUT view directions (use_viewdirs=False: output_linear 256 -> out_ch on
  * h7, nerf.py:50-55, 108-110): the forward-with-save stops after layer 7 (h7 is the last stored layer input, raw =
  * [nrows, out_ch]); the chain starts from d_h7 = (d_raw W_out) * [h7 > 0] computed on CUDA cores and runs W7^T..W1^T;

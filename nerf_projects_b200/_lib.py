@@ -53,6 +53,7 @@ _SIGS = {
     "nerfb_pack_weights_bwd": ([C.POINTER(_vp), _vp, _vp], _i),
     "nerfb_mlp_bwd_chain_bf16": ([_ll, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_mlp_wgrad_bf16": ([_ll, _vp, _vp, _vp, C.POINTER(_vp), _vp], _i),
+    "nerfb_mlp_bwd_fused_bf16": ([_ll, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp, _i, _i, _vp], _i),
     "nerfb_mlp_fwd_save_nv_bf16": ([_i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "nerfb_pack_weights_bwd_nv": ([C.POINTER(_vp), _i, _vp, _vp], _i),
     "nerfb_mlp_bwd_chain_nv_bf16": ([_ll, _vp, _vp, _vp, _vp, _vp, _vp], _i),

@@ -37,6 +37,7 @@
 #include "tc05.cuh"
 #include "mlp_layout.cuh"
 #include "composite.cuh"
+#include "wgrad_body.cuh"
 
 namespace nerfb {
 using namespace tc05;
@@ -182,6 +183,8 @@ struct MlpArgs {
   const float* d_raw4; // MODE_BWD without view directions: gradient of output channel 4 [nrows] or null
   int param_off;      // byte offset of the fp32 parameter block inside `packed`
   int bias_off;       // byte offset of the bias-tile area inside `packed` (forward modes)
+  int* flags;         // MODE_BWD inside the fused backward launch: completion flags [ntiles][kFlagGroups][2] for the
+  int epoch;          //   weight-gradient CTAs (wgrad_body.cuh), set to `epoch` when a half's bulk stores have completed
   // MODE_FWD_COMP: compositing folded into the forward
   int lindisp;        // z == nullptr: coarse depths computed in-kernel from the rays' near / far (z_at)
   float zstep;        // fl(1 / (S - 1)): torch.linspace's step for those depths
@@ -369,10 +372,8 @@ __device__ __noinline__ void composite_tile(const MlpArgs& a, const float4* __re
 
 // -------------------------------------------------------------- kernel
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc,
-                const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
-                const __grid_constant__ CUtensorMap tm32) {
+__device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, const CUtensorMap& tm128, const CUtensorMap& tm64,
+                                         const CUtensorMap& tm32) {
   constexpr bool SAVE = (MODE == MODE_FWD_SAVE || MODE == MODE_FWD_SAVE_NV);
   constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_BWD_NV);
   constexpr bool NV = (MODE == MODE_FWD_SAVE_NV || MODE == MODE_BWD_NV);   // training kernels of the no-view-directions network
@@ -601,6 +602,25 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
     // the second one here -- a 64 KB store issued only at the end finished reading shared memory too late and stalled
     // the next publish on its wait_group.read.
     const bool half_leader = (q == 0 && lane == 0);
+    // Fused backward launch (a.flags != nullptr): every (tile, panel group, column half) this thread stores is TWO bulk
+    // groups; when the second one is committed, everything older than the 4 most recent groups -- i.e. the entry before the
+    // previous one -- has completed and its flag is released to the weight-gradient CTAs (two entries of lag: the wait
+    // never stalls the epilogue).
+    int sig_old = -1, sig_prev = -1;
+    auto release_flag = [&](int idx) {
+      asm volatile("fence.proxy.async;" ::: "memory");      // completed async-proxy writes before the generic-proxy flag
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + idx), "r"(a.epoch) : "memory");
+    };
+    auto entry_committed = [&](const uint8_t* gdst) {
+      const size_t off = (size_t)(gdst - a.gstore);
+      const size_t T = off / kBwdTileBytes;
+      const uint32_t in = (uint32_t)(off - T * kBwdTileBytes);
+      const int grp = in < (uint32_t)kGFeat ? 0 : (in < (uint32_t)kGY ? 1 : 2 + (int)((in - kGY) / (4 * kPanel)));
+      bulk_wait4();
+      if (sig_old >= 0) release_flag(sig_old);
+      sig_old = sig_prev;
+      sig_prev = (int)((T * kFlagGroups + grp) * 2 + hh);
+    };
     auto publish = [&](int t, bool signal, uint8_t* gdst, int npanels) {
       tc_fence_before();
       fence_proxy_async_smem();
@@ -611,8 +631,16 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
       if (et == 0 && signal) { mbar_arrive_remote(bar(B_ACT + t), 0); tr(2, 0x900 + t); }
       if ((SAVE || BWD) && half_leader && gdst != nullptr) {
         const int pnl = (npanels == 4) ? 2 * hh + 1 : hh;          // 4 panels: my half's second; 2 panels: my chunk
-        bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
-        bulk_commit();
+        if (BWD && a.flags != nullptr && npanels == 2) {          // one panel per half: as two groups, like the others
+          bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel / 2);
+          bulk_commit();
+          bulk_s2g(gdst + pnl * kPanel + kPanel / 2, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes + kPanel / 2, kPanel / 2);
+          bulk_commit();
+        } else {
+          bulk_s2g(gdst + pnl * kPanel, sbase + kSmAct + (t * 4 + pnl) * kChunkBytes, kPanel);
+          bulk_commit();
+        }
+        if (BWD && a.flags != nullptr) entry_committed(gdst);
       }
     };
     // first panel (columns 128*hh .. 128*hh+63) of a 4-panel tile: complete after the second 32-column batch of my half
@@ -1098,13 +1126,40 @@ nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched
         }
       }
     }
-    if ((SAVE || BWD) && half_leader) bulk_wait0();
+    if ((SAVE || BWD) && half_leader) {
+      bulk_wait0();
+      if (BWD && a.flags != nullptr) {
+        if (sig_old >= 0) release_flag(sig_old);
+        if (sig_prev >= 0) release_flag(sig_prev);
+      }
+    }
   }
 
   // ---- teardown
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+nerf_mlp_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc,
+                const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
+                const __grid_constant__ CUtensorMap tm32) {
+  mlp_body<MODE>(a, sc, tm128, tm64, tm32);
+}
+
+// The backward of a network pass in ONE launch: the first `chain_ctas` CTAs (2-CTA clusters) run the data-gradient chain,
+// the others the weight-gradient jobs, which take the chain's dY panels through per-tile completion flags while they are
+// still in L2 (wgrad_body.cuh).  The weight-gradient kernel alone is HBM-bound on reading dY and the layer inputs
+// (10.6 KB per sample); here dY is read from L2 and the tensor work of both halves overlaps.  All CTAs must be
+// co-resident (consumers spin on flags): the launch is cooperative and the grid is the number of SMs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+nerf_bwd_fused_kernel(const __grid_constant__ MlpArgs a, const __grid_constant__ Sched sc,
+                      const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
+                      const __grid_constant__ CUtensorMap tm32, const __grid_constant__ WArgs w, const int chain_ctas) {
+  if ((int)blockIdx.x < chain_ctas) mlp_body<MODE_BWD>(a, sc, tm128, tm64, tm32);
+  else wgrad_body<true>(w, (int)blockIdx.x - chain_ctas);
 }
 
 // ------------------------------------------------------------- packing
@@ -1327,7 +1382,9 @@ static int get_blob_maps(const void* blob, size_t bytes, BlobMaps* out) {   // r
   return NERFB_OK;
 }
 
-static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
+constexpr int MODE_BWD_FUSED = 6;      // launch_mlp only: nerf_bwd_fused_kernel (chain CTAs + weight-gradient CTAs)
+
+static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream, WArgs* wargs = nullptr, int chain_ctas = 0) {
   static Sched sched_vd, sched_novd, sched_bwd, sched_bwd_novd;
   static bool init[64] = {false};           // function attributes are per device
   static std::mutex mu;
@@ -1346,6 +1403,8 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBytes > kWgSmemBytes ? kSmemBytes : kWgSmemBytes));
     init[dev] = true;
   }
   lock.unlock();
@@ -1355,11 +1414,21 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     const int m = atoi(e);
     if (m > 0 && m < a.nclusters) a.nclusters = m;
   }
+  if (mode == MODE_BWD_FUSED) a.nclusters = chain_ctas / 2;
   if (a.nclusters > a.nst) a.nclusters = a.nst;
   a.watch = get_watch();
   a.trace = g_trace;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * a.nclusters);
+  cudaLaunchAttribute coop[1];
+  if (mode == MODE_BWD_FUSED) {
+    NERFB_REQUIRE(wargs != nullptr && a.nclusters == chain_ctas / 2, "fused backward: too few samples for %d chain CTAs", chain_ctas);
+    cfg.gridDim = dim3(sm_count());                       // chain CTAs + weight-gradient CTAs = every SM, all co-resident
+    coop[0].id = cudaLaunchAttributeCooperative;          // ... which the cooperative launch verifies
+    coop[0].val.cooperative = 1;
+    cfg.attrs = coop;
+    cfg.numAttrs = 1;
+  }
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
@@ -1395,6 +1464,12 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream) {
     else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_SAVE_NV>, a, sched_novd, maps->tm128, maps->tm64, maps->tm32));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD_SAVE>");
+  }
+  if (mode == MODE_BWD_FUSED) {
+    cfg.dynamicSmemBytes = kSmemBytes > kWgSmemBytes ? kSmemBytes : kWgSmemBytes;
+    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_bwd_fused_kernel, a, sched_bwd, maps->tm128, maps->tm64, maps->tm32, *wargs, chain_ctas));
+    NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
+    return check_launch("nerf_bwd_fused_kernel");
   }
   if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD>, a, sched_bwd, maps->tm128, maps->tm64, maps->tm32));
   else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_BWD_NV>, a, sched_bwd_novd, maps->tm128, maps->tm64, maps->tm32));
@@ -1515,6 +1590,34 @@ extern "C" int nerfb_mlp_bwd_chain_bf16(long long nrows, const float* d_raw, con
   a.gstore = (uint8_t*)gstore;
   a.d_raw = d_raw;
   return launch_mlp(MODE_BWD, a, true, stream);
+}
+
+extern "C" int nerfb_mlp_bwd_fused_bf16(long long nrows, const float* d_raw_padded, const void* packed_bwd, const void* masks,
+                                        const void* acts, void* gstore, float* const* h_grads, int* flags, int epoch,
+                                        int chain_sms, void* stream) {
+  NERFB_REQUIRE(nrows > 0 && d_raw_padded && packed_bwd && masks && acts && gstore && h_grads && flags,
+                "nerfb_mlp_bwd_fused_bf16: bad arguments");
+  NERFB_REQUIRE(aligned16(d_raw_padded) && aligned16(packed_bwd) && aligned16(masks) && aligned16(gstore) && aligned16(acts),
+                "nerfb_mlp_bwd_fused_bf16: all buffers must be 16-byte aligned");
+  const int sms = sm_count();
+  NERFB_REQUIRE(chain_sms >= 2 && chain_sms % 2 == 0 && sms % 2 == 0 && sms - chain_sms >= kMaxJobs,
+                "nerfb_mlp_bwd_fused_bf16: chain_sms=%d does not split %d SMs", chain_sms, sms);
+  MlpArgs a{};
+  a.nrows = nrows; a.S = 1; a.use_viewdirs = 1; a.out_ch = 4;
+  a.packed = (const uint8_t*)packed_bwd;
+  a.param_off = kChunkAreaBwd;
+  a.masks = (uint8_t*)masks;
+  a.gstore = (uint8_t*)gstore;
+  a.d_raw = d_raw_padded;
+  a.flags = flags;
+  a.epoch = epoch;
+  WArgs w;
+  if (int rc = build_wgrad_args("nerfb_mlp_bwd_fused_bf16", nrows, 1, 4, acts, gstore, d_raw_padded, nullptr, h_grads,
+                                sms - chain_sms, w))
+    return rc;
+  w.flags = flags;
+  w.epoch = epoch;
+  return launch_mlp(MODE_BWD_FUSED, a, true, stream, &w, chain_sms);
 }
 
 // ---- the same three steps for the network WITHOUT view directions (output_linear head, nerf.py:50-55, 108-110)

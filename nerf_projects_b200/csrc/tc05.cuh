@@ -157,6 +157,8 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// all but the 4 most recently committed bulk groups of this thread have COMPLETED (their global writes are done)
+__device__ __forceinline__ void bulk_wait4() { asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); }
 
 // bulk prefetch of a global range into L2 (no destination; fire and forget)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {

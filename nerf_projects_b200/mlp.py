@@ -318,8 +318,21 @@ def _fwd_save(net, R, S, rays, z, pts, viewdirs, packed, raw, acts, masks):
         ops.mlp_fwd_save_nv_bf16(R, S, rays, z, pts, net.output_ch, packed, raw, acts, masks)
 
 
+# Chain + weight gradients in ONE cooperative launch (nerf_bwd_fused_kernel: dY handed over through L2 with per-tile
+# completion flags).  Correct (tests/test_gpu_tc.py::test_fused_backward_launch_equals_separate_kernels) but MEASURED SLOWER
+# than the two launches: 3.27 ms against 0.905 + 1.543 ms on 786 432 samples at the best SM split (profiles/README.md) --
+# the weight-gradient CTAs are bound by their own per-stage rate (~1.5 us per 64-sample stage), not by HBM, so giving half
+# of the SMs to the chain doubles their time.  Kept as an opt-in experiment: NERFB200_FUSED_BWD=1.
+FUSED_BWD = os.environ.get("NERFB200_FUSED_BWD", "0") == "1"
+FUSED_BWD_CHAIN_SMS = int(os.environ.get("NERFB200_FUSED_BWD_CHAIN_SMS", "68"))
+FUSED_BWD_MIN_ROWS = 1 << 17       # below ~2 chain iterations the single launch has nothing to overlap
+
+
 def _chain_and_wgrad(net, n, d_pad, d4, packed_bwd, acts, masks, gstore, gptrs):
     if net.use_viewdirs:
+        if FUSED_BWD and n >= FUSED_BWD_MIN_ROWS:
+            ops.mlp_bwd_fused_bf16(n, d_pad, packed_bwd, masks, acts, gstore, gptrs, FUSED_BWD_CHAIN_SMS)
+            return
         ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore)
         ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs)
     else:

@@ -379,6 +379,25 @@ def mlp_wgrad_bf16(nrows, acts, gstore, d_raw_padded, grad_ptrs: Sequence[Option
     _count()
 
 
+_bwd_flags = {}
+
+
+def mlp_bwd_fused_bf16(nrows, d_raw_padded, packed_bwd, masks, acts, gstore, grad_ptrs: Sequence[Optional[int]], chain_sms=76):
+    """Data-gradient chain + weight gradients of one network pass in ONE cooperative launch (nerf_bwd_fused_kernel)."""
+    dev = acts.device
+    need = 4 * ((int(nrows) + 511) // 512) * 20
+    ent = _bwd_flags.get(dev)
+    if ent is None or ent[0].numel() < need:
+        ent = [torch.zeros(max(need, 1 << 16), dtype=torch.int32, device=dev), 0]
+        _bwd_flags[dev] = ent
+    ent[1] += 1
+    arr = (C.c_void_p * L.NERFB_NUM_PARAMS)(*[p if p else None for p in grad_ptrs])
+    L.check(L.load().nerfb_mlp_bwd_fused_bf16(int(nrows), L.ptr(d_raw_padded), L.ptr(packed_bwd), L.ptr(masks), L.ptr(acts),
+                                              L.ptr(gstore), arr, L.ptr(ent[0]), int(ent[1]), int(chain_sms), L.stream()),
+            "nerfb_mlp_bwd_fused_bf16")
+    _count()
+
+
 # no view directions (output_linear head): d_raw is [nrows,4] = channels 0..3, d_raw4 [nrows] = channel 4 or None
 
 def pack_weights_bwd_nv(param_ptrs: Sequence[Optional[int]], out_ch: int, packed_bwd: torch.Tensor):

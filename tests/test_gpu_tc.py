@@ -353,6 +353,39 @@ def test_tc_backward_many_chunks_matches_fp32_kernels():
     assert all(_rel(g_tc[k], g_tc2[k]) < 1e-4 for k in g_tc)
 
 
+@pytest.mark.parametrize("R,S,chain_sms", [(2048, 192, 76), (4096, 64, 76), (1000, 192, 48), (3001, 192, 100)])
+def test_fused_backward_launch_equals_separate_kernels(R, S, chain_sms):
+    """nerf_bwd_fused_kernel (data-gradient chain + weight gradients in ONE cooperative launch, dY handed over through
+    per-tile completion flags while it is in L2) against the two separate launches on the same saved forward: identical
+    gstore bytes, gradients equal up to the order of the fp32 atomics; twice in a row (the flags buffer is reused with a new
+    epoch), ragged sizes (padded last super-tile) and other SM splits."""
+    from nerf_projects_b200 import mlp, ops, _lib
+    params, rays, z, d_raw = _train_case(R, S, seed=21)
+    net = _net(params, True, 5)
+    rays, z, d_raw = rays.to(DEV), z.to(DEV), d_raw.to(DEV)
+    n = R * S
+    try:
+        raw, (acts, masks) = mlp.forward_save_bf16(net, R, S, rays, z)
+        d_pad, _ = mlp._padded_d_raw(net, d_raw, n, rays.device)
+        packed_bwd = mlp.packed_weights_bwd(net)
+        g_sep = mlp._zero_grads(net)
+        gstore_a = torch.zeros(ops.train_store_bytes(n, 1), dtype=torch.uint8, device=DEV)
+        ops.mlp_bwd_chain_bf16(n, d_pad, packed_bwd, masks, gstore_a)
+        ops.mlp_wgrad_bf16(n, acts, gstore_a, d_pad, mlp._param_ptrs(g_sep))
+        for rep in range(2):
+            g_fus = mlp._zero_grads(net)
+            gstore_b = torch.zeros(ops.train_store_bytes(n, 1), dtype=torch.uint8, device=DEV)
+            ops.mlp_bwd_fused_bf16(n, d_pad, packed_bwd, masks, acts, gstore_b, mlp._param_ptrs(g_fus), chain_sms)
+            torch.cuda.synchronize()
+            assert torch.equal(gstore_a, gstore_b), "the chain inside the fused launch wrote different gradients"
+            worst = max(_rel(g_fus[k], g_sep[k]) for k in g_sep)
+            print(f"fused vs separate backward (R={R}, S={S}, chain_sms={chain_sms}, run {rep}): worst relative difference {worst:.2e}")
+            assert worst < 5e-4, {k: _rel(g_fus[k], g_sep[k]) for k in g_sep}     # other CTA split = other fp32 summation order
+    except Exception:
+        print("watchdog:", _lib.watchdog_record())
+        raise
+
+
 @pytest.mark.parametrize("R,S", [(1, 64), (3, 192), (700, 64)])
 def test_tc_backward_ragged_sizes_vs_fp32_kernels(R, S):
     """Tiny and ragged batches (one ray; sample counts that are not a multiple of the 512-row super-tile): the padded rows

@@ -43,6 +43,10 @@ legs = {
                   9 * 32 + 38 * 128 + 16),
     "wgrad": (lambda: ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs), 1186816, 10.4 * 1024),
 }
+# the data-gradient chain + weight gradients in one cooperative launch, for several SM splits (chain SMs of 148)
+for cs in (60, 68, 76, 84, 92):
+    legs[f"bwd_fused_{cs}"] = ((lambda cs=cs: ops.mlp_bwd_fused_bf16(n, d_pad, packed_bwd, masks, acts, gstore, gptrs, cs)),
+                               2 * 557696 + 1186816, 9 * 32 + 38 * 128 + 16 + 5 * 1024 + 300)
 if len(sys.argv) > 3 and sys.argv[3] == "nv":
     # network without view directions: output_linear head (492 544 MACs forward, 7 chain layers, 33 + 32 stored panels)
     net = nb.NeRF(8, 256, 63, 0, 5, [4], False).to(dev)
