@@ -512,7 +512,7 @@ def main():
                     "d2h_bytes_per_step": n_rays * 20 * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_kernel<FWD>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_kernel<MODE_FWD_COMP> (fused MLP + in-kernel compositing)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic()[0],
                          "traffic_detail": ncu_traffic()[1],
                          "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
