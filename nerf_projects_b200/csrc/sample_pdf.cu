@@ -87,7 +87,16 @@ __device__ void build_cdf(float* __restrict__ s_w, float* __restrict__ s_cdf, in
   const int seg = (n + 31) / 32;
   const int j0 = min(n, lane * seg), j1 = min(n, j0 + seg);
   double local = 0.0;
-  for (int j = j0; j < j1; ++j) local += (double)__fdiv_rn(s_w[j], S);
+  float pdf[4];                       // a lane's pdf terms (IEEE divisions: computed once when the lane owns <= 4)
+  if (seg <= 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      pdf[t] = (j0 + t < j1) ? __fdiv_rn(s_w[j0 + t], S) : 0.f;
+      if (j0 + t < j1) local += (double)pdf[t];
+    }
+  } else {
+    for (int j = j0; j < j1; ++j) local += (double)__fdiv_rn(s_w[j], S);
+  }
   double incl = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -96,28 +105,96 @@ __device__ void build_cdf(float* __restrict__ s_w, float* __restrict__ s_cdf, in
   }
   double run = incl - local;
   if (lane == 0) s_cdf[0] = 0.f;
-  for (int j = j0; j < j1; ++j) {
-    run += (double)__fdiv_rn(s_w[j], S);
-    s_cdf[j + 1] = (float)run;
+  if (seg <= 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (j0 + t < j1) {
+        run += (double)pdf[t];
+        s_cdf[j0 + t + 1] = (float)run;
+      }
+  } else {
+    for (int j = j0; j < j1; ++j) {
+      run += (double)__fdiv_rn(s_w[j], S);
+      s_cdf[j + 1] = (float)run;
+    }
   }
   __syncwarp();
 }
 
-__device__ __forceinline__ float draw_sample(const float* __restrict__ s_cdf, const float* __restrict__ s_bins,
-                                             int M, float u, int* ind_out) {
-  int lo = 0, hi = M;
-  while (lo < hi) {  // searchsorted(right=True): #{j : cdf[j] <= u}
-    const int mid = (lo + hi) >> 1;
-    if (s_cdf[mid] <= u) lo = mid + 1; else hi = mid;
+// shared-memory accesses by 32-bit shared-window address: with generic `float*` scratch pointers the compiler
+// rematerialises the window base (S2R SR_CgaCtaId + LEA) around every access inside the search loops
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// searchsorted(right=True): #{j : cdf[j] <= u}.  The cdf is non-decreasing (fp64 running sum of non-negative terms,
+// rounded monotonically), so the count is found by descending power-of-two steps -- one load, one compare, one predicated
+// add per step, no data-dependent branch (the lo/hi loop cost 12-14 instructions per step and was 28 % of the resampling
+// kernel's instructions).  TOP = largest power of two <= M when M + 1 is a power of two (every step stays in range, fully
+// unrolled: M = 63 for 64 coarse samples), else 0: `top` at run time with a range check.
+template <int TOP>
+__device__ __forceinline__ int count_le(uint32_t cdf_sa, int M, int top, float u) {
+  if (TOP > 0) {
+    uint32_t p = cdf_sa;                       // address of cdf[lo]
+#pragma unroll
+    for (int step = TOP; step > 0; step >>= 1)
+      if (lds_f32(p + 4u * (uint32_t)(step - 1)) <= u) p += 4u * (uint32_t)step;
+    return (int)((p - cdf_sa) >> 2);
   }
+  int lo = 0;
+  for (int step = top; step > 0; step >>= 1) {
+    const int nxt = lo + step;
+    const float c = (nxt <= M) ? lds_f32(cdf_sa + 4u * (uint32_t)(nxt - 1)) : CUDART_INF_F;
+    if (c <= u) lo = nxt;
+  }
+  return lo;
+}
+
+template <int TOP>
+__device__ __forceinline__ float draw_sample(uint32_t cdf_sa, uint32_t bins_sa, int M, int top, float u, int* ind_out) {
+  const int lo = count_le<TOP>(cdf_sa, M, top, u);
   *ind_out = lo;
   const int below = max(lo - 1, 0), above = min(lo, M - 1);
-  const float c0 = s_cdf[below], c1 = s_cdf[above];
+  const float c0 = lds_f32(cdf_sa + 4u * (uint32_t)below), c1 = lds_f32(cdf_sa + 4u * (uint32_t)above);
   float denom = __fsub_rn(c1, c0);
   if (denom < 1e-5f) denom = 1.0f;
   const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
-  const float b0 = s_bins[below], b1 = s_bins[above];
+  const float b0 = lds_f32(bins_sa + 4u * (uint32_t)below), b1 = lds_f32(bins_sa + 4u * (uint32_t)above);
   return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+}
+
+// draws samples i = lane, lane + 32, ... < N of one ray; f(i, sample, ind) consumes them
+template <typename F>
+__device__ __forceinline__ void draw_all(const float* s_cdf, const float* s_bins, int M, int N, int det, const float* u_row,
+                                         int lane, F&& f) {
+  const uint32_t cdf_sa = (uint32_t)__cvta_generic_to_shared(s_cdf), bins_sa = (uint32_t)__cvta_generic_to_shared(s_bins);
+  const int top = 1 << (31 - __clz(M));
+  // torch.linspace(0, 1, N)[i] (common.cuh: linspace01) with the IEEE division of its step done once per ray
+  const float lstep = (N > 1) ? __fdiv_rn(1.0f, (float)(N - 1)) : 0.f;
+  auto u_at = [&](int i) -> float {
+    if (!det) return u_row[i];
+    if (N <= 1) return 0.f;
+    return (i < N / 2) ? __fmul_rn(lstep, (float)i) : __fmaf_rn(-lstep, (float)(N - 1 - i), 1.0f);
+  };
+  if (M == 63) {
+    for (int i = lane; i < N; i += 32) {
+      int ind;
+      const float s = draw_sample<32>(cdf_sa, bins_sa, M, top, u_at(i), &ind);
+      f(i, s, ind);
+    }
+  } else {
+    for (int i = lane; i < N; i += 32) {
+      int ind;
+      const float s = draw_sample<0>(cdf_sa, bins_sa, M, top, u_at(i), &ind);
+      f(i, s, ind);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(32 * PW)
@@ -135,12 +212,10 @@ sample_pdf_kernel(int R, int M, int N, const float* __restrict__ bins, int ld_bi
   for (int j = lane; j < M; j += 32) s_bins[j] = bins[(size_t)r * ld_bins + j];
   __syncwarp();
   build_cdf(s_w, s_cdf, M, lane);
-  for (int i = lane; i < N; i += 32) {
-    const float u = det ? linspace01(i, N) : u_in[(size_t)r * N + i];
-    int ind;
-    samples[(size_t)r * N + i] = draw_sample(s_cdf, s_bins, M, u, &ind);
+  draw_all(s_cdf, s_bins, M, N, det, det ? nullptr : u_in + (size_t)r * N, lane, [&](int i, float s, int ind) {
+    samples[(size_t)r * N + i] = s;
     if (inds) inds[(size_t)r * N + i] = ind;
-  }
+  });
 }
 
 // The z_mid / sample_pdf / sort / z_std block of render_rays for ONE ray (one warp).  `wr` = the ray's S compositing
@@ -153,27 +228,33 @@ __device__ void hierarchical_z_ray(int S, int N, int P, const float* zr, const f
   float* s_cdf = s_w + M;
   float* s_bins = s_cdf + M;
   float* s_sort = s_bins + M;
-  for (int j = lane; j < M - 1; j += 32) s_w[j] = __fadd_rn(wr[j + 1], 1e-5f);
-  for (int j = lane; j < M; j += 32) s_bins[j] = __fmul_rn(0.5f, __fadd_rn(zr[j + 1], zr[j]));
-  for (int j = lane; j < S; j += 32) s_sort[j] = zr[j];
-  for (int j = S + N + lane; j < P; j += 32) s_sort[j] = CUDART_INF_F;
+  {
+    const uint32_t w_sa = (uint32_t)__cvta_generic_to_shared(s_w), bins_sa = (uint32_t)__cvta_generic_to_shared(s_bins);
+    const uint32_t sort_sa = (uint32_t)__cvta_generic_to_shared(s_sort);
+    for (int j = lane; j < S; j += 32) {
+      const float zj = zr[j];
+      sts_f32(sort_sa + 4u * (uint32_t)j, zj);
+      if (j < M) sts_f32(bins_sa + 4u * (uint32_t)j, __fmul_rn(0.5f, __fadd_rn(zr[j + 1], zj)));
+      if (j < M - 1) sts_f32(w_sa + 4u * (uint32_t)j, __fadd_rn(wr[j + 1], 1e-5f));
+    }
+  }
   __syncwarp();
   build_cdf(s_w, s_cdf, M, lane);
   double sum = 0.0;
-  for (int i = lane; i < N; i += 32) {
-    const float u = det ? linspace01(i, N) : u_row[i];
-    int ind;
-    const float s = draw_sample(s_cdf, s_bins, M, u, &ind);
+  draw_all(s_cdf, s_bins, M, N, det, u_row, lane, [&](int i, float s, int ind) {
     s_sort[S + i] = s;
     sum += (double)s;
     if (z_samples_row) z_samples_row[i] = s;
     if (inds_row) inds_row[i] = ind;
-  }
+  });
   __syncwarp();
   if (z_std) {  // torch.std(unbiased=False): population std of the N new samples
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const double mean = sum / N;
+    // N a power of two (128 by default): the two fp64 divisions are exact scalings (same bits, ~50 instructions fewer)
+    const bool pow2 = (N & (N - 1)) == 0;
+    const double invN = __longlong_as_double((long long)(1023 - (31 - __clz(N))) << 52);
+    const double mean = pow2 ? sum * invN : sum / N;
     double var = 0.0;
     for (int i = lane; i < N; i += 32) {
       const double d = (double)s_sort[S + i] - mean;
@@ -181,62 +262,77 @@ __device__ void hierarchical_z_ray(int S, int N, int P, const float* zr, const f
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    if (lane == 0) *z_std = (float)sqrt(var / N);
+    if (lane == 0) *z_std = (float)sqrt(pow2 ? var * invN : var / N);
   }
-  // torch.sort(cat([z_vals, z_samples])) returns values only, so any correct sort is bit-identical.  When both lists
-  // are already non-decreasing (always for the coarse depths; for the new samples whenever u is sorted, i.e. the
-  // deterministic test-time case, up to last-ulp effects at bin edges) a merge-path merge does it in ~100
-  // instructions per lane; the check below keeps the general bitonic sort as the fallback, so the result never
-  // depends on that assumption.
-  bool a_sorted = true, b_sorted = true;
-  for (int i = lane; i < S + N; i += 32)
-    if (i != 0 && i != S && s_sort[i] < s_sort[i - 1]) { if (i < S) a_sorted = false; else b_sorted = false; }
-  a_sorted = __all_sync(0xffffffffu, a_sorted);
-  b_sorted = __all_sync(0xffffffffu, b_sorted);
-  // random u (training): only the N new samples are out of order -> bitonic sort of those (padded with the +inf already
-  // behind them to PN = pow2 >= N, when that fits the buffer), then the same merge: 112 instead of 288 compare-exchanges
-  // per lane at 64 + 128
-  if (a_sorted && !b_sorted) {
+  // torch.sort(cat([z_vals, z_samples])) returns values only, so any correct sort is bit-identical.  The coarse depths
+  // are non-decreasing, and so are the new samples whenever u is (the deterministic test-time case, up to last-ulp
+  // effects at bin edges); with random u (training) only the N new samples are out of order and are bitonic-sorted first
+  // (112 instead of 288 compare-exchanges per lane at 64 + 128).  A merge-path merge of the two lists then does it in ~100
+  // instructions per lane.  Nothing is ASSUMED: the merge is verified afterwards -- every lane's outputs non-decreasing
+  // and continuing the previous lane's, and every lane ending exactly where the next one started (so the output is a
+  // permutation of the input) -- and any violation falls through to the general bitonic sort.
+  const uint32_t A_sa = (uint32_t)__cvta_generic_to_shared(s_sort), B_sa = A_sa + 4u * (uint32_t)S;
+  bool try_merge = true;
+  if (!det) {
     int PN = 1;
     while (PN < N) PN <<= 1;
     if (S + PN <= P) {
-      float* Bs = s_sort + S;
+      for (int j = S + N + lane; j < S + PN; j += 32) s_sort[j] = CUDART_INF_F;
+      __syncwarp();
       for (int k = 2; k <= PN; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
           for (int t = lane; t < PN; t += 32) {
             const int partner = t ^ j;
             if (partner > t) {
-              const float a = Bs[t], b = Bs[partner];
+              const float a = lds_f32(B_sa + 4u * (uint32_t)t), b = lds_f32(B_sa + 4u * (uint32_t)partner);
               const bool up = ((t & k) == 0);
-              if ((a > b) == up) { Bs[t] = b; Bs[partner] = a; }
+              if ((a > b) == up) { sts_f32(B_sa + 4u * (uint32_t)t, b); sts_f32(B_sa + 4u * (uint32_t)partner, a); }
             }
           }
           __syncwarp();
         }
       }
-      b_sorted = true;
+    } else {
+      try_merge = false;
     }
   }
-  if (a_sorted && b_sorted) {
-    const float* A = s_sort;            // S coarse depths
-    const float* B = s_sort + S;        // N new samples
+  if (try_merge) {
     const int T = S + N, per = (T + 31) / 32;
     const int p0 = min(T, lane * per), p1 = min(T, p0 + per);
     int lo = max(0, p0 - N), hi = min(p0, S);
     while (lo < hi) {                   // number of A elements among the first p0 outputs (A first on ties)
       const int mid = (lo + hi) >> 1;
-      if (A[mid] <= B[p0 - mid - 1]) lo = mid + 1; else hi = mid;
+      if (lds_f32(A_sa + 4u * (uint32_t)mid) <= lds_f32(B_sa + 4u * (uint32_t)(p0 - mid - 1))) lo = mid + 1; else hi = mid;
     }
-    int i = lo, j = p0 - lo;
+    const int i0 = lo, j0 = p0 - lo;
+    // the heads of the two lists stay in registers; one shared-memory load per output
+    uint32_t pa = A_sa + 4u * (uint32_t)i0, pb = B_sa + 4u * (uint32_t)j0;
+    const uint32_t ea = B_sa, eb = B_sa + 4u * (uint32_t)N;
+    float a = (pa < ea) ? lds_f32(pa) : CUDART_INF_F, b = (pb < eb) ? lds_f32(pb) : CUDART_INF_F;
+    float prev = -CUDART_INF_F, first = CUDART_INF_F;
+    bool ok = true;
     float* out = z_out_row;
     for (int p = p0; p < p1; ++p) {
-      const bool take_a = (i < S) && (j >= N || A[i] <= B[j]);
-      out[p] = take_a ? A[i] : B[j];
-      if (take_a) ++i; else ++j;
+      const bool take_a = (pa < ea) && (pb >= eb || a <= b);
+      const float v = take_a ? a : b;
+      out[p] = v;
+      ok = ok && !(v < prev);
+      if (p == p0) first = v;
+      prev = v;
+      if (take_a) { pa += 4u; a = (pa < ea) ? lds_f32(pa) : CUDART_INF_F; } else { pb += 4u; b = (pb < eb) ? lds_f32(pb) : CUDART_INF_F; }
     }
-    return;
+    // seams: my end = the next lane's start (in both lists), and my first output >= the previous lane's last
+    const int iend = (int)((pa - A_sa) >> 2), jend = (int)((pb - B_sa) >> 2);
+    const int inext = __shfl_down_sync(0xffffffffu, i0, 1), jnext = __shfl_down_sync(0xffffffffu, j0, 1);
+    const float last_prev = __shfl_up_sync(0xffffffffu, prev, 1);
+    if (lane < 31) ok = ok && iend == inext && jend == jnext;
+    else ok = ok && iend == S && jend == N;
+    if (lane > 0 && p1 > p0) ok = ok && !(first < last_prev);
+    if (__all_sync(0xffffffffu, ok)) return;
   }
   // general case: warp bitonic sort over P = pow2 >= S+N
+  for (int j = S + N + lane; j < P; j += 32) s_sort[j] = CUDART_INF_F;
+  __syncwarp();
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = lane; t < P; t += 32) {
