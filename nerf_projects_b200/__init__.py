@@ -17,7 +17,7 @@ calling an op without the built library or without a CUDA device raises.
 from ._lib import NerfB200Error, LIB_PATH, load as load_library  # noqa: F401
 from .embedder import Embedder, get_embedder  # noqa: F401
 from .model import NeRF  # noqa: F401
-from .mlp import get_precision, set_precision  # noqa: F401
+from .mlp import get_precision, precision, release_workspaces, set_precision  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .render import (batchify, batchify_rays, create_nerf, get_rays, get_rays_np, img2mse, mse2psnr,  # noqa: F401
                      ndc_rays, raw2outputs, render, render_path, render_rays, run_network, sample_pdf, to8b)
@@ -32,7 +32,7 @@ from . import ops  # noqa: F401
 
 __all__ = ["render", "render_rays", "batchify_rays", "render_path", "run_network", "batchify", "raw2outputs",
            "create_nerf", "NeRF", "Embedder", "get_embedder", "get_rays", "get_rays_np", "ndc_rays", "sample_pdf",
-           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids",
+           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "precision", "release_workspaces", "FusedAdam", "NerfB200Error", "RayBatcher", "precrop_pixel_ids",
            "keyed_rng", "step_seed", "calculate_ssim", "calculate_metrics", "calculate_lpips",
            "load_blender_data", "load_llff_data", "load_LINEMOD_data", "load_dv_data", "pose_spherical", "train",
            "Args", "default_config", "load_config", "save_config", "AttrDict", "load_yaml", "save_yaml",

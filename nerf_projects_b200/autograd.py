@@ -72,7 +72,7 @@ class RenderRaysFn(Function):
     """The fused render_rays (ipynb:359-492): coarse pass, compositing,
     hierarchical sampling, fine pass, compositing -- differentiable w.r.t. the
     parameters of both networks.  Forward stores rays, depths, the 4-channel raw
-    outputs and -- bf16 mode, when they fit mlp.SAVE_BUDGET_BYTES -- the bf16 layer
+    outputs and -- bf16 mode, when they fit mlp._save_budget_bytes() -- the bf16 layer
     inputs of each pass for the tensor-core backward; otherwise the backward
     recomputes the MLP activations chunk by chunk.
 

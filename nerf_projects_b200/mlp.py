@@ -10,7 +10,9 @@ Two precisions, both hand-written CUDA:
 """
 from __future__ import annotations
 
+import contextlib
 import os
+import threading
 from typing import Dict, List, Optional
 
 import torch
@@ -23,15 +25,32 @@ ROWS_PER_CHUNK = 1 << 18      # rows (ray samples) processed per fp32 chunk
 
 
 def set_precision(mode: str):
-    """'bf16' (tensor cores, default) or 'fp32' (validation mode, 1e-4 parity)."""
+    """'bf16' (tensor cores, default) or 'fp32' (validation mode, 1e-4 parity).  Sets the process-wide default;
+    `precision(mode)` overrides it for the current thread inside a `with` block."""
     global _PRECISION
     if mode not in ("bf16", "fp32"):
         raise ValueError("precision must be 'bf16' or 'fp32'")
     _PRECISION = mode
 
 
+_tls = threading.local()
+
+
 def get_precision() -> str:
-    return _PRECISION
+    return getattr(_tls, "mode", None) or _PRECISION
+
+
+@contextlib.contextmanager
+def precision(mode: str):
+    """Scoped, thread-local precision: `with nb.precision("fp32"): render(...)` leaves the process default untouched."""
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    prev = getattr(_tls, "mode", None)
+    _tls.mode = mode
+    try:
+        yield
+    finally:
+        _tls.mode = prev
 
 
 def param_list(net) -> List[torch.Tensor]:
@@ -216,7 +235,7 @@ def forward_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
 
 
 def forward(net, R, S, rays, z, pts=None, viewdirs=None):
-    if _PRECISION == "bf16":
+    if get_precision() == "bf16":
         return forward_bf16(net, R, S, rays, z, pts, viewdirs)
     return forward_fp32(net, R, S, rays, z, pts, viewdirs)
 
@@ -367,14 +386,24 @@ def backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw) -> Dict[str, torch.T
     return grads
 
 
-SAVE_BUDGET_BYTES = int(os.environ.get("NERFB200_SAVE_BUDGET_GB", "24")) << 30
+def _save_budget_bytes(dev=None) -> int:
+    """Bytes the training forward may keep for the backward: NERFB200_SAVE_BUDGET_GB if set, else the smaller of 24 GB and
+    a quarter of the device's memory (a 4096-ray step needs 10 GB; larger steps recompute chunk by chunk)."""
+    env = os.environ.get("NERFB200_SAVE_BUDGET_GB")
+    if env is not None:
+        return int(float(env) * (1 << 30))
+    total = torch.cuda.get_device_properties(dev if dev is not None else torch.cuda.current_device()).total_memory
+    return min(24 << 30, total // 4)
+
+
 
 
 def can_save_forward(net, nrows: int) -> bool:
     """Training forward may keep its layer inputs (5 KB per sample) for the backward instead of
     recomputing them, when the tile stores of this pass fit the budget."""
-    return (_PRECISION == "bf16" and supports_bf16_backward(net)
-            and ops.train_store_bytes(nrows, 0) + ops.train_store_bytes(nrows, 1) <= SAVE_BUDGET_BYTES)
+    return (get_precision() == "bf16" and supports_bf16_backward(net)
+            and ops.train_store_bytes(nrows, 0) + ops.train_store_bytes(nrows, 1)
+            <= _save_budget_bytes(net.pts_linears[0].weight.device))
 
 
 def forward_save_bf16(net, R, S, rays, z, pts=None, viewdirs=None):
@@ -403,6 +432,6 @@ def backward_from_saved(net, nrows: int, saved, d_raw) -> Dict[str, torch.Tensor
 def backward(net, R, S, rays, z, pts, viewdirs, d_raw):
     """bf16 mode: tensor-core backward for the canonical 8x256 network (either head), fp32 CUDA-core kernels
     otherwise (other architectures, validation mode)."""
-    if _PRECISION == "bf16" and supports_bf16_backward(net):
+    if get_precision() == "bf16" and supports_bf16_backward(net):
         return backward_bf16(net, R, S, rays, z, pts, viewdirs, d_raw)
     return backward_fp32(net, R, S, rays, z, pts, viewdirs, d_raw)

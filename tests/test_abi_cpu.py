@@ -120,3 +120,23 @@ def test_library_sass_uses_the_blackwell_tensor_and_copy_engines():
     for op, at_least in (("UTCHMMA", 50), ("LDTM", 10), ("UTCBAR", 5), ("UTMALDG", 2), ("UBLKCP", 5)):
         assert sass.count(op) >= at_least, f"{op}: {sass.count(op)} occurrences"
     assert "HMMA.16816" not in sass and "WGMMA" not in sass          # no legacy warp-level tensor-core path
+
+
+def test_precision_override_is_scoped_and_thread_local():
+    """`with precision(...)` overrides the process default for the current thread only (process-global state)."""
+    import threading
+
+    import nerf_projects_b200 as nb
+    base = nb.get_precision()
+    seen = {}
+    with nb.precision("fp32"):
+        assert nb.get_precision() == "fp32"
+        t = threading.Thread(target=lambda: seen.setdefault("other", nb.get_precision()))
+        t.start(); t.join()
+        with nb.precision("bf16"):
+            assert nb.get_precision() == "bf16"
+        assert nb.get_precision() == "fp32"
+    assert nb.get_precision() == base and seen["other"] == base
+    with pytest.raises(ValueError):
+        with nb.precision("fp16"):
+            pass
