@@ -224,6 +224,18 @@ def test_hierarchical_z_vs_oracle():
         z_ref = torch.sort(torch.cat([zt, T(zs_ref)], -1), -1)[0]
         z_out, _, _, _ = ops.hierarchical_z(cu(z), cu(w), N, det=False, u=cu(u))
         assert np.array_equal(npy(z_out), z_ref.numpy())
+        # coarse depths that are NOT sorted (never produced by render_rays, but torch.sort does not care): the merge's
+        # after-the-fact verification must reject its own output and the general sort must take over
+        z_bad = z.copy()
+        z_bad[:, [3, S - 5]] = z_bad[:, [S - 5, 3]]
+        z_bad[::3, S // 2] = 9.0
+        zb = T(z_bad)
+        zb_mid = .5 * (zb[..., 1:] + zb[..., :-1])
+        for det_, u_ in ((True, None), (False, u)):
+            zs_ref, _, _ = SP.sample_pdf_np(zb_mid.numpy(), w[:, 1:-1], N, u=u_)
+            z_ref = torch.sort(torch.cat([zb, T(zs_ref)], -1), -1)[0]
+            z_out, _, _, _ = ops.hierarchical_z(cu(z_bad), cu(w), N, det=det_, u=None if u_ is None else cu(u_))
+            assert np.array_equal(npy(z_out), z_ref.numpy())
 
 
 def test_fused_adam_vs_torch_adam():
