@@ -48,6 +48,7 @@ class Raw2OutputsFn(Function):
     @staticmethod
     def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd: bool):
         raw, z_vals, rays_d = L.f32c(raw), L.f32c(z_vals), L.f32c(rays_d)
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None in backward, not as zero-filled tensors
         rgb, disp, acc, weights, depth = ops.raw2outputs_fwd(raw, z_vals, rays_d, noise, white_bkgd)
         ctx.white = white_bkgd
         ctx.save_for_backward(raw, z_vals, rays_d, noise)
@@ -88,6 +89,9 @@ class RenderRaysFn(Function):
         S, N_imp = cfg["N_samples"], cfg["N_importance"]
         white = cfg["white_bkgd"]
         rays_d = rays[:, 3:6]
+        # outputs the loss does not use (disp, acc, depth, raw under retraw=True, ...) arrive in backward as None instead
+        # of freshly zero-filled tensors: a dozen fills and one [R, S, 4] add fewer per training step
+        ctx.set_materialize_grads(False)
         z_c = ops.coarse_z(rays, S, cfg["lindisp"], t_rand)
         # training: keep the layer inputs of each pass for the backward when they fit (else recompute there)
         # (cfg["train"] is decided by the caller, where grad mode is visible: inside Function.forward grad mode is
