@@ -392,7 +392,13 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
 
   if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xA11, sbase, 0);
   // debug timeline: blocks 0 (leader) and 1 (peer) of cluster 0; 4 regions each: loader, MMA, epilogue, relay/observer
+  // in-kernel clock64 timeline (tools/trace_mlp.py): compiled in only with -DNERFB_TRACE=1 (variant build) -- as a run-time
+  // flag its predicated hooks were 0.8-1.1 % of the executed instructions of every launch
+#ifdef NERFB_TRACE
   const bool tracing = (a.trace != nullptr) && blockIdx.x < 2;
+#else
+  constexpr bool tracing = false;
+#endif
   const int tr_base = blockIdx.x * 4;
   int tr_n = 0;
   auto tr = [&](int region, int tag) {

@@ -1,5 +1,11 @@
-"""Timeline of the fused MLP kernel (block 0): prints per-event cycle offsets (debug aid)."""
+"""Timeline of the fused MLP kernel (block 0): prints per-event cycle offsets (debug aid).
+
+The clock64 hooks are compiled in only with -DNERFB_TRACE=1; build and select that variant first:
+    NERFB_VARIANT=trace NERFB_DEFINES="-DNERFB_TRACE=1" python -m nerf_projects_b200.build
+    NERFB_VARIANT=trace python tools/trace_mlp.py [fwd|save|chain]"""
 import sys, os
+if os.environ.get("NERFB_VARIANT") != "trace":
+    sys.exit("run with NERFB_VARIANT=trace (see the docstring): the product library has no trace hooks")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import nerf_projects_b200 as nb
