@@ -190,7 +190,20 @@ struct MlpArgs {
   float zstep;        // fl(1 / (S - 1)): torch.linspace's step for those depths
   float* comp_rec;    // [R][S/32][kRecFloats] segment records
   float* comp_wpart;  // [R*S] alpha * (exclusive product inside the segment), or null (final pass)
+  // row index -> ray index without a 64-bit division per row (filled by launch_mlp): for nrows < 2^32 and S >= 2,
+  // row / S = (t + ((row - t) >> 1)) >> div_shift with t = umulhi(div_mul, row) (Granlund-Montgomery, exact); else div_mul = 0
+  uint32_t div_mul; int div_shift;
 };
+
+// ray index of a row (row < nrows)
+__device__ __forceinline__ long long row_to_ray(const MlpArgs& a, long long grow) {
+  if (a.div_mul != 0u) {
+    const uint32_t n = (uint32_t)grow;
+    const uint32_t t = __umulhi(a.div_mul, n);
+    return (long long)((t + ((n - t) >> 1)) >> a.div_shift);
+  }
+  return a.S == 1 ? grow : grow / a.S;
+}
 constexpr int kTraceLen = 4096;
 
 // The fp32 parameter block of the network a launch evaluates, ALSO in the constant bank: the final epilogue
@@ -667,7 +680,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
         if (a.pts != nullptr) {
           p[0] = __ldg(a.pts + grow * 3 + 0); p[1] = __ldg(a.pts + grow * 3 + 1); p[2] = __ldg(a.pts + grow * 3 + 2);
         } else {
-          const long long r = grow / a.S;
+          const long long r = row_to_ray(a, grow);
           const float* ray = a.rays + r * a.rw;
           const float zz = (COMP && a.z == nullptr)
                                ? z_at_step((int)(grow - r * a.S), a.S, a.zstep, __ldg(ray + 6), __ldg(ray + 7), a.lindisp)
@@ -680,7 +693,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
     auto load_dir = [&](long long grow, float (&p)[3]) {
       p[0] = p[1] = p[2] = 0.f;
       if (grow < a.nrows) {
-        const long long r = grow / a.S;
+        const long long r = row_to_ray(a, grow);
         const float* src = a.viewdirs != nullptr ? a.viewdirs + r * 3 : a.rays + r * a.rw + 8;
         p[0] = __ldg(src); p[1] = __ldg(src + 1); p[2] = __ldg(src + 2);
       }
@@ -1415,6 +1428,13 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream, WArgs* wargs 
   }
   lock.unlock();
   a.nst = (int)((a.nrows + kSuperRows - 1) / kSuperRows);
+  a.div_mul = 0u; a.div_shift = 0;
+  if (a.S >= 2 && a.nrows < (1ll << 32)) {
+    int l = 0;
+    while ((1ll << l) < (long long)a.S) ++l;                                      // ceil(log2 S) >= 1
+    a.div_mul = (uint32_t)((((1ull << l) - (unsigned long long)a.S) << 32) / (unsigned long long)a.S + 1ull);
+    a.div_shift = l - 1;
+  }
   a.nclusters = sm_count() / 2;
   if (const char* e = getenv("NERFB_MAX_CLUSTERS")) {      // experiments only (contention studies)
     const int m = atoi(e);
