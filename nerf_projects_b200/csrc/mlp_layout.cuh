@@ -90,7 +90,10 @@ constexpr int kChunkAreaBwd = kNumBwdChunks * kChunkFull;
 // *_NV: the network without view directions (output_linear head) -- separate instantiations, so the view-dependent
 // training kernels compile exactly as before
 // MODE_FWD_COMP: the forward with the alpha compositing of raw2outputs folded in (inference): raw is never written
-enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2, MODE_FWD_SAVE_NV = 3, MODE_BWD_NV = 4, MODE_FWD_COMP = 5 };
+// MODE_FWD_NV / MODE_FWD_COMP_NV: the inference kernels of the network without view directions, as their own
+// instantiations: use_viewdirs is a compile-time constant in every kernel, so none carries the other head's epilogue
+enum { MODE_FWD = 0, MODE_FWD_SAVE = 1, MODE_BWD = 2, MODE_FWD_SAVE_NV = 3, MODE_BWD_NV = 4, MODE_FWD_COMP = 5,
+       MODE_FWD_NV = 6, MODE_FWD_COMP_NV = 7 };
 // compositing records: per ray and 32-sample segment 8 floats = {Q = product of 1-alpha+1e-10 over the segment, unused,
 // sum w', sum w' r, sum w' g, sum w' b, sum w' z, unused} with w' = alpha * (exclusive product inside the segment)
 constexpr int kRecFloats = 8;

@@ -390,7 +390,8 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
   constexpr bool SAVE = (MODE == MODE_FWD_SAVE || MODE == MODE_FWD_SAVE_NV);
   constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_BWD_NV);
   constexpr bool NV = (MODE == MODE_FWD_SAVE_NV || MODE == MODE_BWD_NV);   // training kernels of the no-view-directions network
-  constexpr bool COMP = (MODE == MODE_FWD_COMP);                            // forward + compositing (inference)
+  constexpr bool COMP = (MODE == MODE_FWD_COMP || MODE == MODE_FWD_COMP_NV);   // forward + compositing (inference)
+  constexpr bool kVD = !(NV || MODE == MODE_FWD_NV || MODE == MODE_FWD_COMP_NV);   // view-dependent head (compile time)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -500,7 +501,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
     // ===================== compositors: warp 3 takes tile 0, warp 2 tile 1 (two SM schedulers share the cost); each
     // consumes the [rgb logits, sigma] stage of its tile once the epilogue publishes it
     const int t = 3 - warp;
-    const bool vdc = a.use_viewdirs != 0;
+    constexpr bool vdc = kVD;
     const float4* stage = (vdc ? reinterpret_cast<const float4*>(s_par + kOffHeadW + 256)
                                : reinterpret_cast<const float4*>(smem + kSmEnc + 8192)) + t * 128;
     for (int it = 0; it < niter; ++it) {
@@ -606,7 +607,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     uint32_t done_cnt[2] = {0, 0};
     uint32_t enc_cnt = 0;
-    const bool vd = a.use_viewdirs != 0;
+    constexpr bool vd = kVD;
 
     auto enc_wait = [&]() {
       if (enc_cnt > 0) mbar_wait(bar(B_ENC), (enc_cnt - 1) & 1, a.watch, 0x600 + enc_cnt);
@@ -1418,6 +1419,8 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream, WArgs* wargs 
     build_schedule_bwd(false, sched_bwd_novd);
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_COMP_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     NERFB_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<MODE_FWD_SAVE_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -1478,11 +1481,13 @@ static int launch_mlp(int mode, MlpArgs& a, bool vd, void* stream, WArgs* wargs 
   const size_t blob_bytes = (size_t)a.param_off + kParamBytes;
   if (int rc = get_blob_maps(a.packed, blob_bytes, &maps_v)) return rc;
   if (mode == MODE_FWD) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64, maps->tm32));
+    if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD>, a, sched_vd, maps->tm128, maps->tm64, maps->tm32));
+    else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_NV>, a, sched_novd, maps->tm128, maps->tm64, maps->tm32));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD>");
   } else if (mode == MODE_FWD_COMP) {
-    NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_COMP>, a, vd ? sched_vd : sched_novd, maps->tm128, maps->tm64, maps->tm32));
+    if (vd) NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_COMP>, a, sched_vd, maps->tm128, maps->tm64, maps->tm32));
+    else NERFB_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_kernel<MODE_FWD_COMP_NV>, a, sched_novd, maps->tm128, maps->tm64, maps->tm32));
     NERFB_CUDA(cudaEventRecord(g_const_event, cfg.stream));
     return check_launch("nerf_mlp_kernel<FWD_COMP>");
   } else if (mode == MODE_FWD_SAVE) {
