@@ -60,7 +60,12 @@ struct WArgs {
   const float* d_raw4;     // SIMT_OUT with out_ch = 5: gradient of output channel 4, [ntiles*128] (zero padded) or null
   int out_ch;              // SIMT_OUT: rows of output_linear
   long long nstages;       // 2 per 128-sample tile
-  int cta_begin[kMaxJobs + 1];   // CTAs [cta_begin[j], cta_begin[j+1]) split job j's stages evenly: ONE work item per CTA
+  int cta_begin[kMaxJobs + 1];   // fused launch: CTAs [cta_begin[j], cta_begin[j+1]) take job j's tiles round-robin
+  // stand-alone kernel: the jobs laid end to end on a COST timeline (job j = nstages * weight_j units starting at
+  // cost_begin[j]); CTA c of ncta takes the stages whose start falls into [c, c + 1) * cost_total / ncta -- one work item
+  // for most CTAs, two (the tail of one job and the head of the next) for the ~njobs CTAs that straddle a job boundary
+  long long cost_begin[kMaxJobs + 1];
+  int ncta;
   Watch watch;
   const int* flags;        // fused launch: [ntiles][kFlagGroups][2]
   int epoch;
@@ -79,7 +84,7 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
   const uint32_t sbase = smem_u32(smem);
   uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem + kWgSmBars + 64);   // (dynamic: the fused launch has no room for static shared memory)
   auto bar = [&](int i) -> uint32_t { return sbase + kWgSmBars + 8 * i; };
-  const int B_FULL = 0, B_EMPTY = kWgStages, B_ACC = 2 * kWgStages;
+  const int B_FULL = 0, B_EMPTY = kWgStages, B_ACC = 2 * kWgStages, B_TFREE = 2 * kWgStages + 1;
 
   if ((sbase & 1023u) != 0) watchdog_fire(a.watch, 0xB11, sbase, 0);
   if (tid == 0) {
@@ -88,6 +93,7 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
       mbar_init(bar(B_EMPTY + s), 1 + 4);     // tcgen05.commit + one arrive per SIMT warp
     }
     mbar_init(bar(B_ACC), 1);
+    mbar_init(bar(B_TFREE), 4);               // the four draining warps, between two work items of a CTA
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -99,91 +105,131 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  // ---- my work item: job jmine, stages [s0, s1) (the CTAs of a job split its stages evenly)
-  int jmine = 0;
-  while (jmine + 1 < a.njobs && vblock >= a.cta_begin[jmine + 1]) ++jmine;
-  const int nsplit = a.cta_begin[jmine + 1] - a.cta_begin[jmine], isplit = vblock - a.cta_begin[jmine];
-  const long long s0 = a.nstages * isplit / nsplit, s1 = a.nstages * (isplit + 1) / nsplit;
-  const long long ntiles = a.nstages >> 1;
-  // my stages: g = 0 .. nmine-1 -> global stage index stage_of(g) (2 stages = the two 64-row halves of a tile)
-  const long long nmine = FUSED ? (isplit < ntiles ? 2 * ((ntiles - 1 - isplit) / nsplit + 1) : 0) : (s1 - s0);
-  auto stage_of = [&](long long g) -> long long {
-    return FUSED ? 2 * ((long long)isplit + (g >> 1) * nsplit) + (g & 1) : s0 + g;
+  // ---- my work items: (job, stages).  Stand-alone kernel: my slice of the cost timeline (1 or 2 items); fused launch: ONE
+  // item, job jmine's tiles isplit, isplit + nsplit, ... (2 stages = the two 64-row halves of a tile)
+  int item_job[2] = {0, 0};
+  long long item_s0[2] = {0, 0}, item_n[2] = {0, 0};
+  int nitems = 0;
+  int nsplit = 1, isplit = 0;
+  if (FUSED) {
+    int jmine = 0;
+    while (jmine + 1 < a.njobs && vblock >= a.cta_begin[jmine + 1]) ++jmine;
+    nsplit = a.cta_begin[jmine + 1] - a.cta_begin[jmine];
+    isplit = vblock - a.cta_begin[jmine];
+    const long long ntiles = a.nstages >> 1;
+    item_job[0] = jmine;
+    item_n[0] = isplit < ntiles ? 2 * ((ntiles - 1 - isplit) / nsplit + 1) : 0;
+    nitems = item_n[0] > 0 ? 1 : 0;
+  } else if (a.ncta == 0) {
+    // small launches: the CTAs of a job split its stages evenly, ONE item (one TMEM drain) per CTA
+    int jmine = 0;
+    while (jmine + 1 < a.njobs && vblock >= a.cta_begin[jmine + 1]) ++jmine;
+    const int ns = a.cta_begin[jmine + 1] - a.cta_begin[jmine], is = vblock - a.cta_begin[jmine];
+    const long long s0 = a.nstages * is / ns, s1 = a.nstages * (is + 1) / ns;
+    item_job[0] = jmine; item_s0[0] = s0; item_n[0] = s1 - s0;
+    nitems = s1 > s0 ? 1 : 0;
+  } else {
+    const long long T = a.cost_begin[a.njobs];
+    const long long lo = T * vblock / a.ncta, hi = T * (vblock + 1) / a.ncta;
+    for (int j = 0; j < a.njobs && nitems < 2; ++j) {
+      const long long c0 = a.cost_begin[j], wj = a.jobs[j].weight;
+      long long b0 = lo <= c0 ? 0 : (lo - c0 + wj - 1) / wj, b1 = hi <= c0 ? 0 : (hi - c0 + wj - 1) / wj;   // first stage starting at or after lo / hi
+      if (b0 > a.nstages) b0 = a.nstages;
+      if (b1 > a.nstages) b1 = a.nstages;
+      if (b1 > b0) { item_job[nitems] = j; item_s0[nitems] = b0; item_n[nitems] = b1 - b0; ++nitems; }
+    }
+  }
+  // global stage index of stage g of item it
+  auto stage_of = [&](int it, long long g) -> long long {
+    return FUSED ? 2 * ((long long)isplit + (g >> 1) * nsplit) + (g & 1) : item_s0[it] + g;
   };
-  const bool has_work = nmine > 0;
-  const WJob& jb = a.jobs[jmine];
+  const bool has_work = nitems > 0;
 
   if (warp == 0) {
-    // ===================== loader
+    // ===================== loader (gg = position in the stage ring, running across my items)
     if (lane == 0 && has_work) {
-      const int npan = jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + jb.x_panels;
-      for (long long g = 0; g < nmine; ++g) {
-        const long long s = stage_of(g);
-        const int slot = (int)(g % kWgStages);
-        if (FUSED && (g & 1) == 0 && jb.a_panels > 0) {
-          // the chain's bulk stores of this tile's dY panels (both column halves) have completed: acquire the flags,
-          // then order the async-proxy reads below after them
-          const int* f = a.flags + ((size_t)(s >> 1) * kFlagGroups + jb.flag_grp) * 2;
-          const long long t0 = clock64();
-          for (int h = 0; h < 2; ++h) {
-            int v;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f + h) : "memory");
-              if (v != a.epoch && clock64() - t0 > kWatchdogCycles)
-                watchdog_fire(a.watch, 0x1200 + jmine, (uint32_t)(s >> 1), (uint32_t)v);
-            } while (v != a.epoch);
+      long long gg = 0;
+      for (int it = 0; it < nitems; ++it) {
+        const int jmine = item_job[it];
+        const WJob& jb = a.jobs[jmine];
+        const int npan = jb.a_panels + jb.b_panels[0] + jb.b_panels[1] + jb.x_panels;
+        for (long long g = 0; g < item_n[it]; ++g, ++gg) {
+          const long long s = stage_of(it, g);
+          const int slot = (int)(gg % kWgStages);
+          if (FUSED && (g & 1) == 0 && jb.a_panels > 0) {
+            // the chain's bulk stores of this tile's dY panels (both column halves) have completed: acquire the flags,
+            // then order the async-proxy reads below after them
+            const int* f = a.flags + ((size_t)(s >> 1) * kFlagGroups + jb.flag_grp) * 2;
+            const long long t0 = clock64();
+            for (int h = 0; h < 2; ++h) {
+              int v;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f + h) : "memory");
+                if (v != a.epoch && clock64() - t0 > kWatchdogCycles)
+                  watchdog_fire(a.watch, 0x1200 + jmine, (uint32_t)(s >> 1), (uint32_t)v);
+              } while (v != a.epoch);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
           }
-          asm volatile("fence.proxy.async;" ::: "memory");
+          if (gg >= kWgStages) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((gg / kWgStages) + 1) & 1), a.watch, 0x1100 + jmine);
+          const uint32_t dst = sbase + slot * kStageStride;
+          const uint32_t fb = bar(B_FULL + slot);
+          mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u +
+                                        ((jb.simt == SIMT_OUT && a.d_raw4 != nullptr) ? (uint32_t)kStageRows * 4u : 0u));
+          const size_t tile = (size_t)(s >> 1), half = (size_t)(s & 1) * kHalfPanel;
+          const uint8_t* gt = a.gstore + tile * kBwdTileBytes + jb.a_off + half;
+          const uint8_t* ft = a.acts + tile * kFwdTileBytes + half;
+          int p = 0;
+          for (int i = 0; i < jb.a_panels; ++i, ++p) bulk_g2s(dst + p * kHalfPanel, gt + (size_t)i * kPanel, kHalfPanel, fb);
+          for (int grp = 0; grp < 2; ++grp)
+            for (int i = 0; i < jb.b_panels[grp]; ++i, ++p)
+              bulk_g2s(dst + p * kHalfPanel, ft + jb.b_off[grp] + (size_t)i * kPanel, kHalfPanel, fb);
+          for (int i = 0; i < jb.x_panels; ++i, ++p)
+            bulk_g2s(dst + p * kHalfPanel, ft + jb.x_off + (size_t)i * kPanel, kHalfPanel, fb);
+          bulk_g2s(dst + kStageDraw, a.d_raw + (size_t)s * kStageRows * 4, 1024, fb);
+          if (jb.simt == SIMT_OUT && a.d_raw4 != nullptr)      // channel 4 slice [64] fp32 behind the 4 staged h7 panels
+            bulk_g2s(dst + 4 * kHalfPanel, a.d_raw4 + (size_t)s * kStageRows, kStageRows * 4, fb);
         }
-        if (g >= kWgStages) mbar_wait(bar(B_EMPTY + slot), (uint32_t)(((g / kWgStages) + 1) & 1), a.watch, 0x1100 + jmine);
-        const uint32_t dst = sbase + slot * kStageStride;
-        const uint32_t fb = bar(B_FULL + slot);
-        mbar_arrive_expect_tx(fb, (uint32_t)npan * kHalfPanel + 1024u +
-                                      ((jb.simt == SIMT_OUT && a.d_raw4 != nullptr) ? (uint32_t)kStageRows * 4u : 0u));
-        const size_t tile = (size_t)(s >> 1), half = (size_t)(s & 1) * kHalfPanel;
-        const uint8_t* gt = a.gstore + tile * kBwdTileBytes + jb.a_off + half;
-        const uint8_t* ft = a.acts + tile * kFwdTileBytes + half;
-        int p = 0;
-        for (int i = 0; i < jb.a_panels; ++i, ++p) bulk_g2s(dst + p * kHalfPanel, gt + (size_t)i * kPanel, kHalfPanel, fb);
-        for (int grp = 0; grp < 2; ++grp)
-          for (int i = 0; i < jb.b_panels[grp]; ++i, ++p)
-            bulk_g2s(dst + p * kHalfPanel, ft + jb.b_off[grp] + (size_t)i * kPanel, kHalfPanel, fb);
-        for (int i = 0; i < jb.x_panels; ++i, ++p)
-          bulk_g2s(dst + p * kHalfPanel, ft + jb.x_off + (size_t)i * kPanel, kHalfPanel, fb);
-        bulk_g2s(dst + kStageDraw, a.d_raw + (size_t)s * kStageRows * 4, 1024, fb);
-        if (jb.simt == SIMT_OUT && a.d_raw4 != nullptr)      // channel 4 slice [64] fp32 behind the 4 staged h7 panels
-          bulk_g2s(dst + 4 * kHalfPanel, a.d_raw4 + (size_t)s * kStageRows, kStageRows * 4, fb);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane)
     if (has_work && elect_one()) {
-      const int nmh = jb.a_panels / 2;
-      const uint32_t idesc0 = make_idesc_bf16_mn(128, 64 * jb.b_panels[0]);
-      const uint32_t idesc1 = make_idesc_bf16_mn(128, jb.b_panels[1] ? 64 * jb.b_panels[1] : 64);
-      for (long long g = 0; g < nmine; ++g) {
-        const int slot = (int)(g % kWgStages);
-        mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1300 + jmine);
-        tc_fence_after();
-        const uint32_t st = sbase + slot * kStageStride;
-        for (int mh = 0; mh < nmh; ++mh) {
-          const uint64_t da = make_sdesc_sw128_mn(st + mh * 2 * kHalfPanel, kHalfPanel);
-          const uint64_t db0 = make_sdesc_sw128_mn(st + jb.a_panels * kHalfPanel, kHalfPanel);
-          const uint32_t acc0 = (g > 0) ? 1u : 0u;
-#pragma unroll
-          for (int k = 0; k < kStageRows / 16; ++k)
-            umma_bf16<1>(tmem_base + mh * 256, da + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc0,
-                         (k > 0) ? 1u : acc0);
-          if (jb.b_panels[1]) {
-            const uint64_t db1 = make_sdesc_sw128_mn(st + (jb.a_panels + jb.b_panels[0]) * kHalfPanel, kHalfPanel);
-            const uint32_t d1 = tmem_base + mh * 256 + 64 * jb.b_panels[0];   // only used with one M half (views)
+      long long gg = 0;
+      for (int it = 0; it < nitems; ++it) {
+        const int jmine = item_job[it];
+        const WJob& jb = a.jobs[jmine];
+        const int nmh = jb.a_panels / 2;
+        const uint32_t idesc0 = make_idesc_bf16_mn(128, 64 * jb.b_panels[0]);
+        const uint32_t idesc1 = make_idesc_bf16_mn(128, jb.b_panels[1] ? 64 * jb.b_panels[1] : 64);
+        if (it > 0) {     // the previous item's accumulators have been drained out of TMEM
+          mbar_wait(bar(B_TFREE), (uint32_t)((it - 1) & 1), a.watch, 0x1600 + jmine);
+          tc_fence_after();
+        }
+        for (long long g = 0; g < item_n[it]; ++g, ++gg) {
+          const int slot = (int)(gg % kWgStages);
+          mbar_wait(bar(B_FULL + slot), (uint32_t)((gg / kWgStages) & 1), a.watch, 0x1300 + jmine);
+          tc_fence_after();
+          const uint32_t st = sbase + slot * kStageStride;
+          for (int mh = 0; mh < nmh; ++mh) {
+            const uint64_t da = make_sdesc_sw128_mn(st + mh * 2 * kHalfPanel, kHalfPanel);
+            const uint64_t db0 = make_sdesc_sw128_mn(st + jb.a_panels * kHalfPanel, kHalfPanel);
+            const uint32_t acc0 = (g > 0) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < kStageRows / 16; ++k)
-              umma_bf16<1>(d1, da + (uint64_t)(k * 128), db1 + (uint64_t)(k * 128), idesc1, (k > 0) ? 1u : acc0);
+              umma_bf16<1>(tmem_base + mh * 256, da + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc0,
+                           (k > 0) ? 1u : acc0);
+            if (jb.b_panels[1]) {
+              const uint64_t db1 = make_sdesc_sw128_mn(st + (jb.a_panels + jb.b_panels[0]) * kHalfPanel, kHalfPanel);
+              const uint32_t d1 = tmem_base + mh * 256 + 64 * jb.b_panels[0];   // only used with one M half (views)
+#pragma unroll
+              for (int k = 0; k < kStageRows / 16; ++k)
+                umma_bf16<1>(d1, da + (uint64_t)(k * 128), db1 + (uint64_t)(k * 128), idesc1, (k > 0) ? 1u : acc0);
+            }
           }
+          umma_commit<1>(bar(B_EMPTY + slot));
+          if (g + 1 == item_n[it]) umma_commit<1>(bar(B_ACC));
         }
-        umma_commit<1>(bar(B_EMPTY + slot));
-        if (g + 1 == nmine) umma_commit<1>(bar(B_ACC));
       }
     }
     __syncwarp();
@@ -192,8 +238,10 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
     const int st_id = tid - 64;                 // 0..127
     const int q = warp & 3;
     const int row_in_half = 32 * q + lane;      // accumulator lane = output feature within the M half
-    if (has_work) {
-      const int j = jmine;
+    long long gg = 0;
+    for (int it = 0; it < nitems; ++it) {
+      const int j = item_job[it];
+      const WJob& jb = a.jobs[j];
       // per-thread SIMT accumulators.  Mapping for 4-panel operands: 16-byte unit u = st_id & 7 (8 columns)
       // of panel (st_id >> 3) & 3, rows r = (st_id >> 5) mod 4; a warp reads 4 full 128-byte rows per LDS.128.
       float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias: 8 columns of dY
@@ -215,11 +263,9 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
         acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]); acc[5] = fmaf(w, __uint_as_float(v.z & 0xFFFF0000u), acc[5]);
         acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]); acc[7] = fmaf(w, __uint_as_float(v.w & 0xFFFF0000u), acc[7]);
       };
-      for (long long g = 0; g < nmine; ++g) {
-        const long long s = stage_of(g);
-        (void)s;
-        const int slot = (int)(g % kWgStages);
-        mbar_wait(bar(B_FULL + slot), (uint32_t)((g / kWgStages) & 1), a.watch, 0x1400 + j);
+      for (long long g = 0; g < item_n[it]; ++g, ++gg) {
+        const int slot = (int)(gg % kWgStages);
+        mbar_wait(bar(B_FULL + slot), (uint32_t)((gg / kWgStages) & 1), a.watch, 0x1400 + j);
         const uint8_t* stp = smem + slot * kStageStride;
         const float4* draw = reinterpret_cast<const float4*>(stp + kStageDraw);
         if (do_bias) {
@@ -301,7 +347,7 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
         }
       }
       // ---- drain the accumulators: dW[out, col_off + c] += D[out, c]
-      mbar_wait(bar(B_ACC), 0u, a.watch, 0x1500 + j);
+      mbar_wait(bar(B_ACC), (uint32_t)(it & 1), a.watch, 0x1500 + j);
       tc_fence_after();
       const int nmh = jb.a_panels / 2;
       for (int mh = 0; mh < nmh; ++mh) {
@@ -329,9 +375,13 @@ __device__ __forceinline__ void wgrad_body(const WArgs& a, const int vblock) {
           cbase += ncol_g;
         }
       }
+      if (it + 1 < nitems) {      // hand TMEM back to the MMA issuer for my next item
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_TFREE));
+      }
     }
   }
-
 
   tc_fence_before();
   __syncthreads();
@@ -449,6 +499,22 @@ inline int build_wgrad_args(const char* who, long long nrows, int use_viewdirs, 
     }
     a.cta_begin[0] = 0;
     for (int j = 0; j < a.njobs; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + cnt[j];
+  }
+  // cost timeline of the stand-alone kernel (one CTA's slice must not span more than two jobs).  The ~njobs CTAs that
+  // straddle a job boundary drain TMEM twice (35-150 us each), so the timeline pays only when a CTA's share of the stages
+  // is long against a drain: measured break-even ~650 k samples (profiles/README.md); below it the jobs get whole CTAs
+  long long timeline_min = 10000;                      // stages (64 samples each)
+  if (const char* e = getenv("NERFB_WG_TIMELINE_MIN")) timeline_min = atoll(e);
+  a.ncta = a.nstages >= timeline_min ? grid : 0;
+  a.cost_begin[0] = 0;
+  {
+    long long total_w = 0;
+    for (int j = 0; j < a.njobs; ++j) total_w += a.jobs[j].weight;
+    for (int j = 0; j < a.njobs; ++j) {
+      NERFB_REQUIRE(a.jobs[j].weight >= 1 && (long long)a.jobs[j].weight * grid >= total_w,
+                    "%s: job %d (weight %d) is smaller than one CTA's share of %d CTAs", who, j, a.jobs[j].weight, grid);
+      a.cost_begin[j + 1] = a.cost_begin[j] + (long long)a.jobs[j].weight * a.nstages;
+    }
   }
   for (int j = 0; j < a.njobs; ++j) {
     const uint32_t off = a.jobs[j].a_off;
