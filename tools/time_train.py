@@ -44,7 +44,7 @@ legs = {
     "wgrad": (lambda: ops.mlp_wgrad_bf16(n, acts, gstore, d_pad, gptrs), 1186816, 10.4 * 1024),
 }
 # the data-gradient chain + weight gradients in one cooperative launch, for several SM splits (chain SMs of 148)
-for cs in (60, 68, 76, 84, 92):
+for cs in ((60, 68, 76, 84, 92) if R >= 2048 and "--no-fused" not in sys.argv else ()):
     legs[f"bwd_fused_{cs}"] = ((lambda cs=cs: ops.mlp_bwd_fused_bf16(n, d_pad, packed_bwd, masks, acts, gstore, gptrs, cs)),
                                2 * 557696 + 1186816, 9 * 32 + 38 * 128 + 16 + 5 * 1024 + 300)
 if len(sys.argv) > 3 and sys.argv[3] == "nv":
