@@ -386,6 +386,32 @@ def test_fused_backward_launch_equals_separate_kernels(R, S, chain_sms):
         raise
 
 
+@pytest.mark.parametrize("R,S,vd", [(40, 192, True), (331, 64, True), (7, 192, True), (150, 64, False)])
+def test_wgrad_cost_timeline_equals_whole_cta_split(R, S, vd, monkeypatch):
+    """The weight-gradient kernel's two work splits -- whole CTAs per job (small launches) and the cost timeline, where the
+    CTAs that straddle a job boundary run TWO work items with a TMEM drain in between (launches of >= 10 000 stages; forced
+    here with NERFB_WG_TIMELINE_MIN=0) -- on the same stored tensors: equal up to the order of the fp32 reductions, for
+    ragged sizes (slices of a single stage, CTAs without work) and both heads."""
+    from nerf_projects_b200 import mlp, ops, _lib
+    params, rays, z, d_raw = _train_case(R, S, seed=23) if vd else _train_case_nv(R, S, 5, seed=23)
+    net = _net(params, vd, 5)
+    rays, z, d_raw = rays.to(DEV), z.to(DEV), d_raw.to(DEV)
+    n = R * S
+    try:
+        raw, (acts, masks) = mlp.forward_save_bf16(net, R, S, rays, z)
+        grads = {}
+        for mode, tmin in (("whole", "1000000000"), ("timeline", "0")):
+            monkeypatch.setenv("NERFB_WG_TIMELINE_MIN", tmin)
+            grads[mode] = mlp.backward_from_saved(net, n, (acts, masks), d_raw)
+            torch.cuda.synchronize()
+        worst = max(_rel(grads["timeline"][k], grads["whole"][k]) for k in grads["whole"])
+        print(f"wgrad timeline vs whole-CTA split (R={R}, S={S}, viewdirs={vd}): worst relative difference {worst:.2e}")
+        assert worst < 5e-4, {k: _rel(grads["timeline"][k], grads["whole"][k]) for k in grads["whole"]}
+    except Exception:
+        print("watchdog:", _lib.watchdog_record())
+        raise
+
+
 @pytest.mark.parametrize("R,S", [(1, 64), (3, 192), (700, 64)])
 def test_tc_backward_ragged_sizes_vs_fp32_kernels(R, S):
     """Tiny and ragged batches (one ray; sample counts that are not a multiple of the 512-row super-tile): the padded rows
