@@ -691,6 +691,41 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
         }
       }
     };
+    // the same in two steps: the global loads now (7 registers), the arithmetic when the point is needed -- the prefetch
+    // for the next super-tile (layer 6) must not wait for its own loads (an FMUL on the loaded ray was a top stall site)
+    auto load_point_raw = [&](long long grow, float (&q)[7]) {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) q[j] = 0.f;
+      if (grow < a.nrows) {
+        if (a.pts != nullptr) {
+          q[0] = __ldg(a.pts + grow * 3 + 0); q[1] = __ldg(a.pts + grow * 3 + 1); q[2] = __ldg(a.pts + grow * 3 + 2);
+        } else {
+          const long long r = row_to_ray(a, grow);
+          const float* ray = a.rays + r * a.rw;
+          if (COMP && a.z == nullptr) {
+            // coarse depths computed in-kernel: keep near / far and the sample index (as a float: exact below 2^24)
+            q[6] = (float)(int)(grow - r * a.S);
+          } else {
+            q[6] = __ldg(a.z + grow);
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { q[j] = __ldg(ray + j); q[3 + j] = __ldg(ray + 3 + j); }
+        }
+      }
+    };
+    auto finish_point = [&](long long grow, const float (&q)[7], float (&p)[3]) {
+      p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+      if (grow < a.nrows && a.pts == nullptr) {
+        float zz = q[6];
+        if (COMP && a.z == nullptr) {
+          const long long r = row_to_ray(a, grow);
+          const float* ray = a.rays + r * a.rw;
+          zz = z_at_step((int)q[6], a.S, a.zstep, __ldg(ray + 6), __ldg(ray + 7), a.lindisp);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) p[j] = __fadd_rn(q[j], __fmul_rn(q[3 + j], zz));
+      }
+    };
     auto load_dir = [&](long long grow, float (&p)[3]) {
       p[0] = p[1] = p[2] = 0.f;
       if (grow < a.nrows) {
@@ -737,7 +772,9 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
         signal_ready(t);
       }
     }
-    float pnext[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // sample positions of my rows in the NEXT super-tile
+    // rays / depths of my rows in the NEXT super-tile (loaded layers ahead, see load_point_raw); one named array per tile:
+    // indexed by the run-time tile number they would live in local memory, and the store would wait for the loads
+    float qnext0[7] = {}, qnext1[7] = {};
     for (int it = 0; it < niter; ++it) {
       const long long st = cluster_id + (long long)it * a.nclusters;
       long long grow[2];
@@ -948,7 +985,10 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
             enc_wait(); write_enc_x(grow[t], nullptr);
           }
           if (l == 6 && it + 1 < niter)       // global loads whose latency must not sit in front of the next encode
-            load_point((st + a.nclusters) * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row, pnext[t]);
+          {
+            const long long gn = (st + a.nclusters) * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
+            if (t == 0) load_point_raw(gn, qnext0); else load_point_raw(gn, qnext1);
+          }
           if (l == 8) { enc_wait(); write_enc_d(grow[t], SAVE ? gtile[t] + kFDg : nullptr); }
           if (et == 0) tr(2, 0x800 + l * 2 + t);
           if (l + 1 < sc.nlayers) {
@@ -971,7 +1011,12 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
                 asm volatile("bar.sync 1, 256;" ::: "memory");
               }
               const long long stn = st + a.nclusters;
-              write_first_layer_x(t, pnext[t],
+              float pn[3];
+              float qn[7];
+#pragma unroll
+              for (int j = 0; j < 7; ++j) qn[j] = t == 0 ? qnext0[j] : qnext1[j];
+              finish_point(stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row, qn, pn);
+              write_first_layer_x(t, pn,
                                   SAVE ? a.acts + (size_t)(stn * 4 + 2 * t + rank) * kFwdTileBytes + kFXg : nullptr);
               signal_ready(t);
             } else {
