@@ -777,18 +777,15 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
     float qnext0[7] = {}, qnext1[7] = {};
     for (int it = 0; it < niter; ++it) {
       const long long st = cluster_id + (long long)it * a.nclusters;
-      long long grow[2];
-      grow[0] = st * kSuperRows + rank * kTileRows + row;
-      grow[1] = grow[0] + 2 * kTileRows;
-      // global 128-row tile index of (tile t, this CTA) and its training store
-      uint8_t* gtile[2] = {nullptr, nullptr};
-      uint8_t* mtile[2] = {nullptr, nullptr};
-      if (SAVE) {
-        gtile[0] = a.acts + (size_t)(st * 4 + rank) * kFwdTileBytes;
-        gtile[1] = a.acts + (size_t)(st * 4 + 2 + rank) * kFwdTileBytes;
-        mtile[0] = a.masks + (size_t)(st * 4 + rank) * kMaskTileBytes;
-        mtile[1] = a.masks + (size_t)(st * 4 + 2 + rank) * kMaskTileBytes;
-      }
+      // my row of tile t, and (training) the tile's stores: computed from the tile-0 value where they are used -- as
+      // arrays indexed by the run-time tile number they lived in local memory, and the address arithmetic behind the LDL was
+      // a long-scoreboard stall site of the forward-with-save epilogue (profiles/README.md)
+      const long long grow0 = st * kSuperRows + rank * kTileRows + row;
+      uint8_t* const gtile0 = SAVE ? a.acts + (size_t)(st * 4 + rank) * kFwdTileBytes : nullptr;
+      uint8_t* const mtile0 = SAVE ? a.masks + (size_t)(st * 4 + rank) * kMaskTileBytes : nullptr;
+#define GROW(t) (grow0 + (long long)(t) * (2 * kTileRows))
+#define GTILE(t) (gtile0 + (size_t)(t) * (2 * (size_t)kFwdTileBytes))
+#define MTILE(t) (mtile0 + (size_t)(t) * (2 * (size_t)kMaskTileBytes))
       for (int l = 0; l < sc.nlayers; ++l) {
         for (int t = 0; t < 2; ++t) {
           mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + l * 2 + t);
@@ -860,14 +857,14 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
               const int col0 = 128 * hh + 32 * b;
 #ifndef NERFB_EXP_NOSTS
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
-              if (SAVE && b == 1) store_first_panel(t, gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat));
+              if (SAVE && b == 1) store_first_panel(t, GTILE(t) + (l < 8 ? kFH + l * 4 * kPanel : kFFeat));
 #else
               if (w[0] == 0x12345678u) store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
 #endif
             }
             if (l == 7) s_sig[(t * 2 + hh) * 128 + row] = sig;
             if (SAVE && l < 8)
-              *reinterpret_cast<uint4*>(mtile[t] + ((size_t)l * 128 + row) * kMaskRowBytes + 16 * hh) =
+              *reinterpret_cast<uint4*>(MTILE(t) + ((size_t)l * 128 + row) * kMaskRowBytes + 16 * hh) =
                   make_uint4(sbits[0], sbits[1], sbits[2], sbits[3]);
             if (SAVE && NV && out_head) {
               // the two column halves meet in the (idle) enc buffer: [tile][half][row][8]
@@ -875,9 +872,9 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
 #pragma unroll
               for (int k = 0; k < 5; ++k) xch[((t * 2 + hh) * 128 + row) * 8 + k] = part[k];
               asm volatile("bar.sync 1, 256;" ::: "memory");
-              if (hh == 0 && grow[t] < a.nrows) {
+              if (hh == 0 && GROW(t) < a.nrows) {
                 for (int k = 0; k < a.out_ch; ++k)
-                  a.raw[grow[t] * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
+                  a.raw[GROW(t) * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
                                                   xch[((t * 2 + 1) * 128 + row) * 8 + k] + s_par[kOffHeadB + k];
               }
             }
@@ -915,9 +912,9 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
 #pragma unroll
             for (int k = 0; k < 5; ++k) xch[((t * 2 + hh) * 128 + row) * 8 + k] = part[k];
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (hh == 0 && grow[t] < a.nrows) {
+            if (hh == 0 && GROW(t) < a.nrows) {
               for (int k = 0; k < a.out_ch; ++k)
-                a.raw[grow[t] * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
+                a.raw[GROW(t) * a.out_ch + k] = xch[((t * 2 + 0) * 128 + row) * 8 + k] +
                                                 xch[((t * 2 + 1) * 128 + row) * 8 + k] + s_par[kOffHeadB + k];
             }
             }
@@ -943,12 +940,12 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
                   uint32_t w[16];
 #pragma unroll
                   for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(xs[2 * i], xs[2 * i + 1]);
-                  store_row32(gtile[t] + kFHv + hh * kPanel, row, 4 * b, w);
+                  store_row32(GTILE(t) + kFHv + hh * kPanel, row, 4 * b, w);
                 }
               }
               const float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2];
               if (SAVE)
-                *reinterpret_cast<uint2*>(mtile[t] + ((size_t)8 * 128 + row) * kMaskRowBytes + 8 * hh) =
+                *reinterpret_cast<uint2*>(MTILE(t) + ((size_t)8 * 128 + row) * kMaskRowBytes + 8 * hh) =
                     make_uint2(sbits[0], sbits[1]);
               if constexpr (COMP) {
                 // stage [tile][row] float4 in the unused output_linear rows of the parameter block: the hh == 1 partial
@@ -967,9 +964,9 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
               float* xch = s_par + kOffHeadW + 256 + (t * 128 + row) * 3;
               if (hh == 1) { xch[0] = c0; xch[1] = c1; xch[2] = c2; }
               asm volatile("bar.sync 1, 256;" ::: "memory");
-              if (hh == 0 && grow[t] < a.nrows) {
+              if (hh == 0 && GROW(t) < a.nrows) {
                 const float sigma = s_sig[(t * 2 + 0) * 128 + row] + s_sig[(t * 2 + 1) * 128 + row] + s_par[kOffHeadB];
-                *reinterpret_cast<float4*>(a.raw + grow[t] * 4) =
+                *reinterpret_cast<float4*>(a.raw + GROW(t) * 4) =
                     make_float4(c0 + xch[0] + s_par[kOffRgbB], c1 + xch[1] + s_par[kOffRgbB + 1],
                                 c2 + xch[2] + s_par[kOffRgbB + 2], sigma);
               }
@@ -982,19 +979,19 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
               mbar_wait(bar(B_STFREE + 0), (uint32_t)((it - 1) & 1), a.watch, 0xC20);
               mbar_wait(bar(B_STFREE + 1), (uint32_t)((it - 1) & 1), a.watch, 0xC21);
             }
-            enc_wait(); write_enc_x(grow[t], nullptr);
+            enc_wait(); write_enc_x(GROW(t), nullptr);
           }
           if (l == 6 && it + 1 < niter)       // global loads whose latency must not sit in front of the next encode
           {
             const long long gn = (st + a.nclusters) * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
             if (t == 0) load_point_raw(gn, qnext0); else load_point_raw(gn, qnext1);
           }
-          if (l == 8) { enc_wait(); write_enc_d(grow[t], SAVE ? gtile[t] + kFDg : nullptr); }
+          if (l == 8) { enc_wait(); write_enc_d(GROW(t), SAVE ? GTILE(t) + kFDg : nullptr); }
           if (et == 0) tr(2, 0x800 + l * 2 + t);
           if (l + 1 < sc.nlayers) {
             // training: h_l (l < 8) / feature (l == 8) go to the tile store as written
             uint8_t* gdst = nullptr;
-            if (SAVE) gdst = gtile[t] + (l < 8 ? kFH + l * 4 * kPanel : kFFeat);
+            if (SAVE) gdst = GTILE(t) + (l < 8 ? kFH + l * 4 * kPanel : kFFeat);
             publish(t, true, gdst, 4);
             // MODE_FWD_COMP: the stage this tile's final epilogue wrote in the PREVIOUS super-tile is handed to its
             // compositor warp only now, inside the middle layers, not during the epilogue-bound super-tile boundary
@@ -1003,7 +1000,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
           } else {
             // last layer of this tile.  Without view directions h7 is the last stored layer input: the second panels of
             // both halves go out here (nothing to signal, no MMA follows).
-            if (SAVE && NV) publish(t, false, gtile[t] + kFH + 7 * 4 * kPanel, 4);
+            if (SAVE && NV) publish(t, false, GTILE(t) + kFH + 7 * 4 * kPanel, 4);
             if (it + 1 < niter) {
               // the tile's buffers are free -> layer-0 operand of the NEXT super-tile right away
               if (SAVE) {           // ... once the bulk stores of the last stored layer have left the buffer
@@ -1029,6 +1026,9 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
       }
     }
     } else {
+#undef GROW
+#undef GTILE
+#undef MTILE
       // ================= MODE_BWD: data-gradient chain  d_raw -> d_hv -> d_feature -> dY_7 .. dY_0
       // Layer j of the schedule multiplies by a transposed weight matrix; its epilogue applies the ReLU
       // mask of the layer it lands on (sign bits collected by the forward-with-save pass: 16 bytes per
@@ -1040,48 +1040,53 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
       constexpr int j_first = vdb ? 0 : 2, j_end = 9;
       const float* w_rgb = s_par + kOffRgbW;
       const float* w_alpha = s_par + kOffHeadW;     // alpha_linear.weight, or output_linear.weight [5][256] (rows >= out_ch zero)
-      float4 dr_next[2];      // d_raw row and first-stage sign bits of my rows in the next super-tile, requested layers ahead
-      uint2 mhv_next[2];      // view layer: my 64 columns
-      uint4 mh7_next[2];      // no view directions: h7, my 128 columns
-      float d4_next[2] = {0.f, 0.f};   // no view directions, out_ch = 5: gradient of output channel 4
-      auto prefetch_first_stage = [&](long long stn, int t) {
+      // d_raw row and first-stage sign bits of my rows in the next super-tile, requested layers ahead.  One named struct
+      // per tile: as arrays indexed by the run-time tile number they lived in local memory, and the store behind each
+      // load waited for it -- the prefetch stalled where it was issued
+      struct FirstStage {
+        float4 dr;
+        uint2 mhv;       // view layer: my 64 columns
+        uint4 mh7;       // no view directions: h7, my 128 columns
+        float d4;        // no view directions, out_ch = 5: gradient of output channel 4
+      };
+      FirstStage fs0 = {}, fs1 = {};
+      auto prefetch_into = [&](long long stn, int t, FirstStage& f) {
         const long long gn = stn * kSuperRows + rank * kTileRows + 2 * t * kTileRows + row;
         const uint8_t* mt = a.masks + (size_t)(stn * 4 + 2 * t + rank) * kMaskTileBytes;
-        dr_next[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        d4_next[t] = 0.f;
+        f.dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        f.d4 = 0.f;
         if (gn < a.nrows) {
-          dr_next[t] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + gn);
-          if (!vdb && a.d_raw4 != nullptr) d4_next[t] = __ldg(a.d_raw4 + gn);
+          f.dr = __ldg(reinterpret_cast<const float4*>(a.d_raw) + gn);
+          if (!vdb && a.d_raw4 != nullptr) f.d4 = __ldg(a.d_raw4 + gn);
         }
-        if (vdb) mhv_next[t] = __ldg(reinterpret_cast<const uint2*>(mt + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
-        else mh7_next[t] = __ldg(reinterpret_cast<const uint4*>(mt + ((size_t)7 * 128 + row) * kMaskRowBytes + 16 * hh));
+        if (vdb) f.mhv = __ldg(reinterpret_cast<const uint2*>(mt + ((size_t)8 * 128 + row) * kMaskRowBytes) + hh);
+        else f.mh7 = __ldg(reinterpret_cast<const uint4*>(mt + ((size_t)7 * 128 + row) * kMaskRowBytes + 16 * hh));
+      };
+      auto prefetch_first_stage = [&](long long stn, int t) {
+        if (t == 0) prefetch_into(stn, 0, fs0); else prefetch_into(stn, 1, fs1);
       };
       for (int it = 0; it < niter; ++it) {
         const long long st = cluster_id + (long long)it * a.nclusters;
-        long long grow[2];
-        grow[0] = st * kSuperRows + rank * kTileRows + row;
-        grow[1] = grow[0] + 2 * kTileRows;
-        const uint8_t* mtile[2];
-        uint8_t* gtile[2];
-        for (int t = 0; t < 2; ++t) {
-          const size_t T = (size_t)(st * 4 + 2 * t + rank);
-          mtile[t] = a.masks + T * kMaskTileBytes;
-          gtile[t] = a.gstore + T * kBwdTileBytes;
-        }
+        const long long grow0 = st * kSuperRows + rank * kTileRows + row;
+        const uint8_t* const mtile0 = a.masks + (size_t)(st * 4 + rank) * kMaskTileBytes;
+        uint8_t* const gtile0 = a.gstore + (size_t)(st * 4 + rank) * kBwdTileBytes;
+#define GROW(t) (grow0 + (long long)(t) * (2 * kTileRows))
+#define GTILE(t) (gtile0 + (size_t)(t) * (2 * (size_t)kBwdTileBytes))
+#define MTILE(t) (mtile0 + (size_t)(t) * (2 * (size_t)kMaskTileBytes))
         float dsig[2];
         if (it == 0) {        // first super-tile: nothing was prefetched yet
           for (int t = 0; t < 2; ++t) prefetch_first_stage(st, t);
         }
         for (int t = 0; t < 2; ++t) {
-          const float4 dr = dr_next[t];
+          const float4 dr = t == 0 ? fs0.dr : fs1.dr;
           dsig[t] = dr.w;
           if (!vdb) {
             // ---- d_h7 = (sum_k d_raw[k] W_out[k,:]) * [h7 > 0]: my 128 columns (chunks 2hh, 2hh+1) of the K=256 operand
-            const float d4 = d4_next[t];
-            const uint4 m7 = mh7_next[t];
+            const float d4 = t == 0 ? fs0.d4 : fs1.d4;
+            const uint4 m7 = t == 0 ? fs0.mh7 : fs1.mh7;
             const uint32_t m7v[4] = {m7.x, m7.y, m7.z, m7.w};
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
-            uint8_t* gdst = gtile[t] + kGY + 7 * 4 * kPanel;
+            uint8_t* gdst = GTILE(t) + kGY + 7 * 4 * kPanel;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
               const float* wo = w_alpha + 128 * hh + 32 * b;
@@ -1109,7 +1114,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
           }
           // ---- d_hv = (d_rgb W_rgb) * [hv > 0]: my 64 columns (chunk hh) of the K=128 operand
           // hv sign bits: 4 words for columns 0..127; my chunk uses words 2*hh and 2*hh+1
-          const uint2 mhv = mhv_next[t];
+          const uint2 mhv = t == 0 ? fs0.mhv : fs1.mhv;
           uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {          // 32 columns at a time
@@ -1124,12 +1129,12 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
             apply_sign_mask32(w, half == 0 ? mhv.x : mhv.y);
             store_row32(act_t + hh * kChunkBytes, row, 4 * half, w);
           }
-          publish(t, true, gtile[t] + kGHv, 2);
+          publish(t, true, GTILE(t) + kGHv, 2);
         }
         // the 16 bytes of sign bits a thread needs for a tile-layer are requested one whole epilogue ahead (the chain
         // is epilogue-bound, so a load issued right before its use would expose the full DRAM latency every time)
         auto load_mask_words = [&](int jj, int tt) -> uint4 {
-          return __ldg(reinterpret_cast<const uint4*>(mtile[tt] + ((size_t)(8 - jj) * 128 + row) * kMaskRowBytes + 16 * hh));
+          return __ldg(reinterpret_cast<const uint4*>(MTILE(tt) + ((size_t)(8 - jj) * 128 + row) * kMaskRowBytes + 16 * hh));
         };
         uint4 mw_next = load_mask_words(vdb ? 1 : 2, 0);         // first masked tile-layer: j = 1 (2 without views), t = 0
         for (int j = j_first; j < j_end; ++j) {
@@ -1182,10 +1187,10 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
                 prefetch_first_stage(st + a.nclusters, t);
               const int col0 = colbase + 32 * b;
               store_row32(act_t + (col0 >> 6) * kChunkBytes, row, (col0 & 63) >> 3, w);
-              if (b == 1) store_first_panel(t, gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel));
+              if (b == 1) store_first_panel(t, GTILE(t) + (j == 0 ? kGFeat : kGY + m * 4 * kPanel));
             }
             if (et == 0) tr(2, 0x800 + j * 2 + t);
-            uint8_t* gdst = gtile[t] + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);
+            uint8_t* gdst = GTILE(t) + (j == 0 ? kGFeat : kGY + m * 4 * kPanel);
             publish(t, j + 1 < j_end, gdst, 4);
           }
         }
@@ -1205,6 +1210,10 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
   cluster_sync_all();
   if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
 }
+
+#undef GROW
+#undef GTILE
+#undef MTILE
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
