@@ -605,7 +605,7 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
     const int q = warp & 3, hh = (warp - 4) >> 2;
     const int row = 32 * q + lane;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-    uint32_t done_cnt[2] = {0, 0};
+    uint32_t done_cnt0 = 0, done_cnt1 = 0;      // (two scalars, not an array indexed by the run-time tile number: registers)
     uint32_t enc_cnt = 0;
     constexpr bool vd = kVD;
 
@@ -788,8 +788,8 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
 #define MTILE(t) (mtile0 + (size_t)(t) * (2 * (size_t)kMaskTileBytes))
       for (int l = 0; l < sc.nlayers; ++l) {
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + l * 2 + t);
-          done_cnt[t]++;
+          mbar_wait(bar(B_DONE + t), (t == 0 ? done_cnt0 : done_cnt1) & 1, a.watch, 0x700 + l * 2 + t);
+          if (t == 0) ++done_cnt0; else ++done_cnt1;
           if (et == 0) tr(2, 0x700 + l * 2 + t);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + t * 256;
@@ -1073,13 +1073,13 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
 #define GROW(t) (grow0 + (long long)(t) * (2 * kTileRows))
 #define GTILE(t) (gtile0 + (size_t)(t) * (2 * (size_t)kBwdTileBytes))
 #define MTILE(t) (mtile0 + (size_t)(t) * (2 * (size_t)kMaskTileBytes))
-        float dsig[2];
+        float dsig0 = 0.f, dsig1 = 0.f;
         if (it == 0) {        // first super-tile: nothing was prefetched yet
           for (int t = 0; t < 2; ++t) prefetch_first_stage(st, t);
         }
         for (int t = 0; t < 2; ++t) {
           const float4 dr = t == 0 ? fs0.dr : fs1.dr;
-          dsig[t] = dr.w;
+          if (t == 0) dsig0 = dr.w; else dsig1 = dr.w;
           if (!vdb) {
             // ---- d_h7 = (sum_k d_raw[k] W_out[k,:]) * [h7 > 0]: my 128 columns (chunks 2hh, 2hh+1) of the K=256 operand
             const float d4 = t == 0 ? fs0.d4 : fs1.d4;
@@ -1152,13 +1152,13 @@ __device__ __forceinline__ void mlp_body(const MlpArgs& a, const Sched& sc, cons
               const int jn = t == 0 ? j : j + 1, tn = t ^ 1;          // next masked tile-layer
               if (jn < j_end) mw_next = load_mask_words(jn, tn);
             }
-            mbar_wait(bar(B_DONE + t), done_cnt[t] & 1, a.watch, 0x700 + j * 2 + t);
-            done_cnt[t]++;
+            mbar_wait(bar(B_DONE + t), (t == 0 ? done_cnt0 : done_cnt1) & 1, a.watch, 0x700 + j * 2 + t);
+            if (t == 0) ++done_cnt0; else ++done_cnt1;
             if (et == 0) tr(2, 0x700 + j * 2 + t);
             tc_fence_after();
             const uint32_t taddr = tmem_base + lane_addr + t * 256;
             uint8_t* act_t = smem + kSmAct + t * 4 * kChunkBytes;
-            const float ds = dsig[t];
+            const float ds = t == 0 ? dsig0 : dsig1;
             const uint32_t mwv[4] = {mw.x, mw.y, mw.z, mw.w};
             uint32_t v[2][32];
             tmem_ld32(taddr + colbase, v[0]);
