@@ -30,11 +30,6 @@ static_assert(kStageStride % 1024 == 0, "stage buffers must keep the swizzle pha
 
 enum { SIMT_NONE = 0, SIMT_ALPHA = 1, SIMT_RGB = 2, SIMT_OUT = 3 };
 
-// 16-byte vector reduction into global memory (one L2 atomic operation for four floats)
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 struct WJob {
   uint32_t a_off;          // gradient panels inside a bwd tile (gstore)
   int a_panels;            // 4 (256 outputs: two M halves) or 2 (128 outputs)
